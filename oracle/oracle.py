@@ -1,0 +1,205 @@
+"""ctypes/numpy front-end of the CPU oracle (oracle/ldpc_oracle.c).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs.  The product package
+(ldpc_erasure_codes_b200) never imports this module.
+
+H matrices are read here with scipy (independently of the library's own C++
+MAT-v5 loader, so the two cross-check each other).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "libldpc_oracle.so")
+_REPO = os.path.dirname(_HERE)
+CODES_DIR = os.path.join(_REPO, "ldpc_erasure_codes_b200", "codes")
+
+# code table: reference ldpc_params rows (OpenCL/device/LDPC_Vlist_data.h:10-14) + the .mat-only code
+CODE_TABLE = {
+    0: dict(name="n2000_k1000", n=2000, k=1000, rs_n=250, rs_k=125),
+    1: dict(name="n2040_k1530", n=2040, k=1530, rs_n=255, rs_k=192),
+    2: dict(name="n4000_k2000", n=4000, k=2000, rs_n=250, rs_k=125),
+}
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "ldpc_oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "-B"])
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_SO)
+        _lib.orc_ldpc_peel.restype = C.c_int
+        _lib.orc_ldpc_peel_u64.restype = C.c_int
+        _lib.orc_ldpc_hybrid.restype = C.c_int
+        _lib.orc_rs_mds_count.restype = C.c_int
+        _lib.orc_rs_gsys.restype = C.c_int
+        _lib.orc_rs_decode.restype = C.c_int
+        _lib.orc_num_threads.restype = C.c_int
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Code:
+    """H in CSR form (0-based, ascending) = the reference's Vlist rows."""
+
+    def __init__(self, H, k=None, name=""):
+        import scipy.sparse as sp
+
+        R = sp.csr_matrix(H)
+        R.sort_indices()
+        self.m, self.n = R.shape
+        self.k = self.n - self.m if k is None else k
+        self.row_ptr = np.ascontiguousarray(R.indptr, dtype=np.int32)
+        self.col_idx = np.ascontiguousarray(R.indices, dtype=np.int32)
+        self.name = name
+
+    @staticmethod
+    def from_mat(path, name=""):
+        import scipy.io as sio
+
+        H = sio.loadmat(path, spmatrix=True)["H_sparse"]
+        return Code(H, name=name or os.path.basename(path))
+
+    @staticmethod
+    def builtin(code_ind: int) -> "Code":
+        t = CODE_TABLE[code_ind]
+        return Code.from_mat(os.path.join(CODES_DIR, t["name"] + ".mat"), name=t["name"])
+
+
+def threefry4x32_20(ctr, key):
+    c = np.asarray(ctr, dtype=np.uint32)
+    k = np.asarray(key, dtype=np.uint32)
+    o = np.zeros(4, dtype=np.uint32)
+    lib().orc_threefry4x32_20(_p(c), _p(k), _p(o))
+    return o
+
+
+def gen_erasures_iid(n, seed, nframes, P=None, p32=None, frame0=0):
+    """flags [nframes][n] u8.  P = numerator/64 (reference rule) or p32 = 32-bit threshold (extension)."""
+    flags = np.zeros((nframes, n), dtype=np.uint8)
+    mode, thr = (0, int(P)) if P is not None else (1, int(p32))
+    lib().orc_gen_erasures_iid(C.c_int(n), C.c_uint32(seed & 0xFFFFFFFF), C.c_int(mode), C.c_uint32(thr),
+                               C.c_uint64(frame0), C.c_int64(nframes), _p(flags))
+    return flags
+
+
+def gen_erasures_bursty(n, seed, nframes, alpha, beta, bias, frame0=0, state=0):
+    flags = np.zeros((nframes, n), dtype=np.uint8)
+    st = C.c_int(state)
+    lib().orc_gen_erasures_bursty(C.c_int(n), C.c_uint32(seed & 0xFFFFFFFF), C.c_double(alpha), C.c_double(beta),
+                                  C.c_double(bias), C.c_uint64(frame0), C.c_int64(nframes), C.byref(st), _p(flags))
+    return flags, st.value
+
+
+def encode(code: Code, info: np.ndarray, nthreads=0) -> np.ndarray:
+    """info [B][k][S] u8 -> codewords [B][n][S] u8."""
+    info = np.ascontiguousarray(info, dtype=np.uint8)
+    B, k, S = info.shape
+    assert k == code.k
+    cw = np.zeros((B, code.n, S), dtype=np.uint8)
+    lib().orc_ldpc_encode_batch(C.c_int(code.n), C.c_int(code.k), _p(code.row_ptr), _p(code.col_idx), C.c_int(S),
+                                C.c_int64(B), _p(info), _p(cw), C.c_int(nthreads))
+    return cw
+
+
+def decode(code: Code, payload: np.ndarray, erased: np.ndarray, max_iter=50, early_stop=True, mode="peel",
+           nthreads=0, inplace=False):
+    """payload [B][n][S], erased [B][n] (u8 flags).  Returns dict(out, payload, erased, fail_sys, iters, status)."""
+    payload = np.array(payload, dtype=np.uint8, order="C", copy=not inplace)
+    erased = np.array(erased, dtype=np.uint8, order="C", copy=not inplace)
+    B, n, S = payload.shape
+    assert n == code.n and erased.shape == (B, n)
+    out = np.zeros((B, code.k, S), dtype=np.uint8)
+    fail = np.zeros(B, dtype=np.uint8)
+    iters = np.zeros(B, dtype=np.int32)
+    status = np.zeros(B, dtype=np.int32)
+    lib().orc_ldpc_decode_batch(C.c_int(code.n), C.c_int(code.k), _p(code.row_ptr), _p(code.col_idx), C.c_int(S),
+                                C.c_int64(B), _p(payload), _p(erased), _p(out), _p(fail), _p(iters), _p(status),
+                                C.c_int(max_iter), C.c_int(1 if early_stop else 0),
+                                C.c_int({"peel": 0, "hybrid": 1}[mode]), C.c_int(nthreads))
+    return dict(out=out, payload=payload, erased=erased, fail_sys=fail, iters=iters, status=status)
+
+
+def peel_single(code: Code, payload, erased, max_iter=50, early_stop=True, u64=False):
+    payload = np.array(payload, dtype=np.uint8, order="C")
+    erased = np.array(erased, dtype=np.uint8, order="C")
+    n, S = payload.shape
+    fn = lib().orc_ldpc_peel_u64 if u64 else lib().orc_ldpc_peel
+    it = fn(C.c_int(code.n), C.c_int(code.k), _p(code.row_ptr), _p(code.col_idx), C.c_int(S), _p(payload), _p(erased),
+            C.c_int(max_iter), C.c_int(1 if early_stop else 0))
+    return payload, erased, it
+
+
+def hybrid_single(code: Code, payload, erased, peel_iter=10, abort_writeback=False):
+    payload = np.array(payload, dtype=np.uint8, order="C")
+    erased = np.array(erased, dtype=np.uint8, order="C")
+    n, S = payload.shape
+    ro = C.c_int(0)
+    st = lib().orc_ldpc_hybrid(C.c_int(code.n), C.c_int(code.k), _p(code.row_ptr), _p(code.col_idx), C.c_int(S),
+                               _p(payload), _p(erased), C.c_int(peel_iter), C.c_int(1 if abort_writeback else 0),
+                               C.byref(ro))
+    return payload, erased, st, ro.value
+
+
+def rs_mds_count(n, rs_n, rs_k, erased):
+    erased = np.ascontiguousarray(erased, dtype=np.uint8)
+    return lib().orc_rs_mds_count(C.c_int(n), C.c_int(rs_n), C.c_int(rs_k), _p(erased))
+
+
+def gf256_tables():
+    mul = np.zeros((256, 256), dtype=np.uint8)
+    inv = np.zeros(255, dtype=np.uint8)
+    log = np.zeros(256, dtype=np.uint8)
+    alog = np.zeros(255, dtype=np.uint8)
+    lib().orc_gf256_tables(_p(mul), _p(inv), _p(log), _p(alog))
+    return dict(mul=mul, inv=inv, log=log, alog=alog)
+
+
+def rs_gsys(n, k):
+    G = np.zeros((k, n), dtype=np.uint8)
+    rc = lib().orc_rs_gsys(C.c_int(n), C.c_int(k), _p(G))
+    assert rc == 0
+    return G
+
+
+def rs_encode(G, info):
+    """info [k][S] -> cw [n][S]."""
+    k, n = G.shape
+    info = np.ascontiguousarray(info, dtype=np.uint8)
+    S = info.shape[1]
+    cw = np.zeros((n, S), dtype=np.uint8)
+    lib().orc_rs_encode(C.c_int(n), C.c_int(k), C.c_int(S), _p(G), _p(info), _p(cw))
+    return cw
+
+
+def rs_decode(G, recv_idx, recv_val):
+    """recv_idx: first k received positions (0-based, ascending); recv_val [k][S] -> (info [k][S], rank_deficient)."""
+    k, n = G.shape
+    recv_idx = np.ascontiguousarray(recv_idx, dtype=np.int32)
+    recv_val = np.ascontiguousarray(recv_val, dtype=np.uint8)
+    S = recv_val.shape[1]
+    out = np.zeros((k, S), dtype=np.uint8)
+    rc = lib().orc_rs_decode(C.c_int(n), C.c_int(k), C.c_int(S), _p(G), _p(recv_idx), _p(recv_val), _p(out))
+    return out, rc
+
+
+def num_threads():
+    return lib().orc_num_threads()
