@@ -1,0 +1,193 @@
+/*
+ * ldpc_cuda.h -- C ABI of libldpc_cuda, the B200-native packet-erasure codec.
+ *
+ * This library stands where the reference's OpenCL host<->device contract
+ * stands (chadac8j/LDPC_Erasure_Codes, OpenCL/host/src/main.cpp): the reference
+ * has no plugin/FFI layer, its boundary is "create context + buffers, set kernel
+ * args, enqueue the data_in / codec / data_out task trio, finish, read back".
+ * Each entry point below names the reference interface it replaces.
+ *
+ * Conventions
+ *   - plain C, no exceptions, no torch / CUDA types in the signatures: device
+ *     buffers are `void*` device pointers OWNED BY THE CALLER, streams are the
+ *     caller's cudaStream_t passed as `void*` (NULL = default stream);
+ *   - every function returns 0 (LDPC_OK) or a negative LDPC_ERR_* code and
+ *     never calls exit() (the reference's checkError() prints and exits,
+ *     main.cpp:493); ldpc_last_error_string() describes the last failure of
+ *     the calling thread;
+ *   - work is enqueued on the caller's stream, no hidden synchronisation
+ *     except in the *_host variants and ldpc_get_stats();
+ *   - a context is bound to one GPU and is thread-compatible (one context per
+ *     GPU per host thread), like the reference's single-threaded host.
+ *
+ * Data layout (the GPU form of the reference's `symbol_type`,
+ * OpenCL/device/ldpc_erasure_decoder_top.cl:38-44 = {ulong symbol[128]; uchar
+ * is_erasure}): structure-of-arrays --
+ *   payload  [B][n][S] bytes, S = symbol_bytes (reference SYM_LEN*8 = 1024),
+ *   erasure mask [B][mask_words] uint32, bit (i & 31) of word (i >> 5) set iff
+ *            symbol i of that codeword is erased (mask_words = ceil(n/32)).
+ * As in the reference (ldpc_erasure_decoder.cl:17-20) an erased symbol's payload
+ * is expected to be all-zero on input; the decoder never reads it, and writes
+ * it only when it recovers the symbol.
+ */
+#ifndef LDPC_CUDA_H
+#define LDPC_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LDPC_CUDA_ABI_VERSION 1
+
+enum {
+    LDPC_OK = 0,
+    LDPC_ERR_ARG = -1,         /* bad argument                                     */
+    LDPC_ERR_IO = -2,          /* cannot open / read the H file                    */
+    LDPC_ERR_FORMAT = -3,      /* not a MAT-v5 file with a usable H_sparse         */
+    LDPC_ERR_CUDA = -4,        /* CUDA runtime / driver error                      */
+    LDPC_ERR_NOMEM = -5,       /* host or device allocation failed                 */
+    LDPC_ERR_UNSUPPORTED = -6, /* code / symbol size outside what the kernels take */
+    LDPC_ERR_NOT_TRIANGULAR = -7 /* encode asked on an H without the staircase diagonal */
+};
+
+/* decode modes: the reference's OpenCL decoder (peeling only) and the MATLAB hybrid */
+enum {
+    LDPC_MODE_PEEL = 0,   /* OpenCL/device/ldpc_erasure_decoder.cl:24-105            */
+    LDPC_MODE_HYBRID = 1  /* Matlab/My_LDPC_HybridML_Erasure_Decoder.m               */
+};
+
+/* erasure models of ldpc_gen_erasures */
+enum {
+    LDPC_ERASURE_IID64 = 0,  /* reference rule: (x0 & 63) < P   (decoder_top.cl:105) */
+    LDPC_ERASURE_IID32 = 1,  /* extension: x0 < floor(p * 2^32), any rate            */
+    LDPC_ERASURE_BURSTY = 2  /* Matlab/Bursty_Error_Channel_Model_Generator.m        */
+};
+
+typedef struct ldpc_ctx ldpc_ctx;
+typedef struct rs_ctx rs_ctx;
+
+typedef struct ldpc_code_info {
+    int32_t n, k, m;          /* code length, information symbols, checks          */
+    int32_t nnz;              /* ones in H                                          */
+    int32_t symbol_bytes;     /* S                                                  */
+    int32_t mask_words;       /* uint32 words of erasure mask per codeword          */
+    int32_t rs_n, rs_k;       /* RS-equivalent block for MDS counting (ldpc_params) */
+    int32_t max_row_weight, max_col_weight;
+    int32_t encode_levels;    /* dependency depth of the back-substitution          */
+    int32_t slice_bytes;      /* W: bytes of a symbol one executor unit carries     */
+    int32_t exec_slots;       /* units resident in shared memory per SM             */
+    int32_t device;
+    int64_t max_batch;        /* codewords one internal chunk processes             */
+} ldpc_code_info;
+
+typedef struct ldpc_erasure_model {
+    int32_t model;            /* LDPC_ERASURE_*                                     */
+    int32_t per_numerator_div_64; /* IID64: P, erase iff (x0 & 63) < P  (host flag -p) */
+    uint32_t threshold32;     /* IID32: erase iff x0 < threshold32                  */
+    double alpha, beta, bias; /* BURSTY: PER in good / bad state, good-state bias   */
+} ldpc_erasure_model;
+
+/* cumulative counters = the reference's error_type pushed through ERROR_STAT
+ * (decoder_top.cl:46-49, perf_tests.cl:233-236) and printed by data_out (:151-156) */
+typedef struct ldpc_stats {
+    int64_t frames;           /* codewords decoded since create / reset             */
+    int64_t ldpc_errors;      /* frames with a systematic symbol still erased       */
+    int64_t rs_errors;        /* RS-equivalent blocks beyond MDS capacity           */
+    int64_t ml_attempts;      /* hybrid mode: frames that entered GF(2) elimination */
+    int64_t ml_failures;      /* hybrid mode: rank-deficient eliminations           */
+} ldpc_stats;
+
+/* ---- context ------------------------------------------------------------------------
+ * Replaces init_opencl() + the ldpc_params table select (main.cpp:439-544, :258-259) and
+ * the code tables baked into the .aocx (OpenCL/device/LDPC_Vlist_data.h).
+ * h_mat_path: MAT-v5 file holding sparse `H_sparse` (the reference's Matlab/ *.mat), or
+ *   NULL to take the built-in code `code_ind` (0 = (2000,1000), 1 = (2040,1530) as in
+ *   host flag -c, 2 = (4000,2000)); built-ins are read from the `codes/` directory that
+ *   ships next to the library (or $LDPC_CUDA_CODES_DIR).
+ * symbol_bytes: S, a multiple of 16.   max_batch: scratch is sized for this many
+ *   codewords; larger calls are processed in chunks of max_batch.                        */
+int ldpc_ctx_create(ldpc_ctx **out, const char *h_mat_path, int code_ind, int symbol_bytes,
+                    int device, int64_t max_batch);
+/* Replaces cleanup() (main.cpp:668-691). */
+int ldpc_ctx_destroy(ldpc_ctx *ctx);
+int ldpc_ctx_info(const ldpc_ctx *ctx, ldpc_code_info *info);
+/* Host copy of H as CSR (row_ptr[m+1], col_idx[nnz], 0-based ascending) = the Vlist rows. */
+int ldpc_ctx_get_csr(const ldpc_ctx *ctx, int32_t *row_ptr, int32_t *col_idx);
+/* Tuning knob for experiments: force the executor's slice width W (16/32/64/...) and slot
+ * count (0 = choose automatically).                                                      */
+int ldpc_ctx_set_exec_geometry(ldpc_ctx *ctx, int slice_bytes, int slots);
+
+/* ---- encoder ------------------------------------------------------------------------
+ * Replaces the encoder task trio data_in -> ldpc_erasure_encoder -> data_out
+ * (OpenCL/device/ldpc_erasure_encoder_top.cl:43-92, ldpc_erasure_encoder.cl:26-95).
+ * d_info [B][k][S] -> d_cw [B][n][S] (systematic symbols first, then the n-k parities). */
+int ldpc_encode(ldpc_ctx *ctx, const void *d_info, void *d_cw, int64_t B, void *stream);
+
+/* ---- erasure channel ----------------------------------------------------------------
+ * Replaces the decoder-side data_in kernel (ldpc_erasure_decoder_top.cl:57-120):
+ * Threefry4x32-20, key {1, seed}, counter 1 + (frame0 + b) * n + symbol.  Writes the
+ * erasure mask of B codewords and, if d_payload != NULL, zeroes the erased symbols of
+ * d_payload [B][n][S] in place (the "erased = all zero" convention).                     */
+int ldpc_gen_erasures(ldpc_ctx *ctx, const ldpc_erasure_model *model, uint32_t seed,
+                      uint64_t frame0, int64_t B, uint32_t *d_mask, void *d_payload, void *stream);
+
+/* ---- decoder ------------------------------------------------------------------------
+ * Replaces the ldpc_erasure_decoder task (args num_iter, code_ind: main.cpp:593-596) plus
+ * the payload side of data_out.  d_cw [B][n][S] and d_mask [B][mask_words] are read only;
+ * d_out [B][k][S] receives the first k symbols after decoding (decoder.cl:97-102);
+ * d_fail [B] (may be NULL) receives 1 where a systematic symbol is still erased
+ * (perf_tests.cl:215-228).  max_iter = the reference's num_iter (sweeps over the checks,
+ * host flag -i, default 50); the decoder reproduces the serial sweep order exactly, so a
+ * binding cap gives the reference's partial result.  In LDPC_MODE_HYBRID max_iter is the
+ * sweep cap before elimination (10 in the MATLAB file) and d_fail additionally covers
+ * rank-deficient eliminations.                                                           */
+int ldpc_decode(ldpc_ctx *ctx, const void *d_cw, const uint32_t *d_mask, void *d_out,
+                uint8_t *d_fail, int max_iter, int mode, int64_t B, void *stream);
+
+/* ---- statistics ---------------------------------------------------------------------
+ * Replaces the ERROR_STAT channel + data_out report (decoder_top.cl:123-158).
+ * Synchronises the context's device.                                                     */
+int ldpc_get_stats(ldpc_ctx *ctx, ldpc_stats *out);
+int ldpc_reset_stats(ldpc_ctx *ctx);
+
+/* ---- host-buffer entry points -------------------------------------------------------
+ * The reference's run() (main.cpp:555-659): blocking host->device copy, kernels, blocking
+ * device->host copy.  Host pointers (pinned memory makes the copies asynchronous and
+ * overlapped; pageable memory works too).  Chunked and pipelined over internal streams. */
+int ldpc_encode_host(ldpc_ctx *ctx, const void *h_info, void *h_cw, int64_t B);
+int ldpc_decode_host(ldpc_ctx *ctx, const void *h_cw, const uint32_t *h_mask, void *h_out,
+                     uint8_t *h_fail, int max_iter, int mode, int64_t B);
+
+/* ---- synthetic payload --------------------------------------------------------------
+ * Counter-based uniform bytes (Threefry key {2, seed}, counter = 16-byte block index +
+ * block0): bench / test input generator, independent of batch sharding.                  */
+int ldpc_fill_random(void *d_dst, int64_t nbytes, uint32_t seed, uint64_t block0, int device,
+                     void *stream);
+
+/* ---- Reed-Solomon GF(2^8) comparison code -------------------------------------------
+ * Field polynomial 0x171, alpha = 2 (Matlab/Build_GF256_Lookup_Tables.m:11-24);
+ * G[i][j] = alpha^(i*j) systematised (Matlab/Test_My_RS_Decode.m:30-37);
+ * decode from the first k received symbols (Matlab/ReedSolomonErasureCodes.m:80-85,
+ * My_RS_Decode_Optimize_With_GFTables.m).                                                */
+int rs_ctx_create(rs_ctx **out, int n, int k, int symbol_bytes, int device, int64_t max_batch);
+int rs_ctx_destroy(rs_ctx *ctx);
+/* Host copy of the k x n systematic generator (row-major). */
+int rs_ctx_get_generator(const rs_ctx *ctx, uint8_t *gsys);
+/* d_info [B][k][S] -> d_cw [B][n][S]. */
+int rs_encode(rs_ctx *ctx, const void *d_info, void *d_cw, int64_t B, void *stream);
+/* d_cw [B][n][S], d_mask [B][ceil(n/32)] -> d_out [B][k][S]; d_fail[b] = 1 iff fewer than
+ * k symbols of codeword b were received (then d_out holds the received systematic symbols,
+ * erased ones zero).                                                                      */
+int rs_decode(rs_ctx *ctx, const void *d_cw, const uint32_t *d_mask, void *d_out,
+              uint8_t *d_fail, int64_t B, void *stream);
+
+/* ---- errors ------------------------------------------------------------------------- */
+const char *ldpc_last_error_string(void);
+int ldpc_cuda_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LDPC_CUDA_H */

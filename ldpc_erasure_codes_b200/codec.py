@@ -1,0 +1,165 @@
+"""Host-side mirror of the reference's host program for the codec path.
+
+The reference drives its kernels from one C++ translation unit (OpenCL/host/src/main.cpp):
+`init_opencl()` -> `run()` (write buffer, set args, enqueue data_in / codec / data_out, finish,
+read buffer) -> `cleanup()`, parameterised by the CLI flags -c (code), -p (PER numerator / 64),
+-n (frames), -i (iterations).  `LdpcCodec` keeps those names and meanings on top of the C ABI
+(include/ldpc_cuda.h); torch is used only for device memory and streams.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+MODE_PEEL, MODE_HYBRID = 0, 1
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class LdpcCodec:
+    """One context on one GPU (ldpc_ctx).  code = built-in index (the host's -c flag: 0 = (2000,1000),
+    1 = (2040,1530); 2 = (4000,2000)) or a path to a MAT-v5 file holding `H_sparse`."""
+
+    def __init__(self, code=1, symbol_bytes=64, device=0, max_batch=65536):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("LdpcCodec needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.device = torch.device("cuda", device)
+        h = C.c_void_p()
+        path = code.encode() if isinstance(code, str) else None
+        ind = code if isinstance(code, int) else 0
+        _lib.check(self.lib.ldpc_ctx_create(C.byref(h), path, ind, symbol_bytes, device, max_batch))
+        self._h = h
+        info = _lib.CodeInfo()
+        _lib.check(self.lib.ldpc_ctx_info(self._h, C.byref(info)))
+        self.info = info
+        self.n, self.k, self.m, self.S = info.n, info.k, info.m, info.symbol_bytes
+        self.mask_words = info.mask_words
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.ldpc_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- code tables -------------------------------------------------------------
+    def csr(self):
+        rp = np.zeros(self.m + 1, np.int32)
+        ci = np.zeros(self.info.nnz, np.int32)
+        _lib.check(self.lib.ldpc_ctx_get_csr(self._h, rp.ctypes.data_as(C.c_void_p), ci.ctypes.data_as(C.c_void_p)))
+        return rp, ci
+
+    def set_exec_geometry(self, slice_bytes=0, slots=0):
+        _lib.check(self.lib.ldpc_ctx_set_exec_geometry(self._h, slice_bytes, slots))
+        _lib.check(self.lib.ldpc_ctx_info(self._h, C.byref(self.info)))
+
+    # ---- encoder trio (encoder_top.cl data_in -> ldpc_erasure_encoder -> data_out) ----
+    def encode(self, info: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        assert info.is_cuda and info.dtype == torch.uint8 and info.is_contiguous()
+        B = info.shape[0]
+        assert info.shape[1:] == (self.k, self.S)
+        if out is None:
+            out = torch.empty((B, self.n, self.S), dtype=torch.uint8, device=info.device)
+        _lib.check(self.lib.ldpc_encode(self._h, _ptr(info), _ptr(out), B, _stream()))
+        return out
+
+    # ---- decoder-side data_in: Threefry erasure channel ---------------------------------
+    def gen_erasures(self, B, seed, P=None, p=None, bursty=None, frame0=0, payload: torch.Tensor | None = None,
+                     mask: torch.Tensor | None = None) -> torch.Tensor:
+        """P = PER numerator / 64 (host flag -p); p = exact rate (32-bit threshold extension);
+        bursty = (alpha, beta, bias).  Zeroes erased symbols of `payload` in place when given."""
+        m = _lib.ErasureModel()
+        if P is not None:
+            m.model, m.per_numerator_div_64 = 0, int(P)
+        elif p is not None:
+            m.model, m.threshold32 = 1, min(int(p * 2 ** 32), 2 ** 32 - 1)
+        else:
+            m.model = 2
+            m.alpha, m.beta, m.bias = bursty
+        if mask is None:
+            mask = torch.empty((B, self.mask_words), dtype=torch.int32, device=self.device)
+        _lib.check(self.lib.ldpc_gen_erasures(self._h, C.byref(m), seed & 0xFFFFFFFF, frame0, B, _ptr(mask),
+                                              _ptr(payload), _stream()))
+        return mask
+
+    # ---- ldpc_erasure_decoder(num_iter, code_ind) + data_out ----------------------------
+    def decode(self, cw: torch.Tensor, mask: torch.Tensor, max_iter=50, mode="peel", out=None, fail=None):
+        assert cw.is_cuda and cw.dtype == torch.uint8 and cw.is_contiguous() and mask.is_contiguous()
+        B = cw.shape[0]
+        assert cw.shape[1:] == (self.n, self.S) and mask.shape == (B, self.mask_words)
+        if out is None:
+            out = torch.empty((B, self.k, self.S), dtype=torch.uint8, device=cw.device)
+        if fail is None:
+            fail = torch.empty((B,), dtype=torch.uint8, device=cw.device)
+        _lib.check(self.lib.ldpc_decode(self._h, _ptr(cw), _ptr(mask), _ptr(out), _ptr(fail), max_iter,
+                                        {"peel": MODE_PEEL, "hybrid": MODE_HYBRID}[mode], B, _stream()))
+        return out, fail
+
+    # ---- run(): host buffers in, host buffers out ---------------------------------------
+    def decode_host(self, cw: torch.Tensor, mask: torch.Tensor, max_iter=50, mode="peel", out=None, fail=None):
+        """cw / mask are HOST tensors (pinned for overlap); copies happen inside the call."""
+        assert not cw.is_cuda and cw.dtype == torch.uint8 and cw.is_contiguous()
+        B = cw.shape[0]
+        if out is None:
+            out = torch.empty((B, self.k, self.S), dtype=torch.uint8, pin_memory=True)
+        if fail is None:
+            fail = torch.empty((B,), dtype=torch.uint8, pin_memory=True)
+        _lib.check(self.lib.ldpc_decode_host(self._h, _ptr(cw), _ptr(mask), _ptr(out), _ptr(fail), max_iter,
+                                             {"peel": MODE_PEEL, "hybrid": MODE_HYBRID}[mode], B))
+        return out, fail
+
+    def encode_host(self, info: torch.Tensor, out=None):
+        assert not info.is_cuda and info.dtype == torch.uint8 and info.is_contiguous()
+        B = info.shape[0]
+        if out is None:
+            out = torch.empty((B, self.n, self.S), dtype=torch.uint8, pin_memory=True)
+        _lib.check(self.lib.ldpc_encode_host(self._h, _ptr(info), _ptr(out), B))
+        return out
+
+    # ---- ERROR_STAT / data_out report ----------------------------------------------------
+    def stats(self):
+        s = _lib.Stats()
+        _lib.check(self.lib.ldpc_get_stats(self._h, C.byref(s)))
+        return {f: getattr(s, f) for f, _ in s._fields_}
+
+    def reset_stats(self):
+        _lib.check(self.lib.ldpc_reset_stats(self._h))
+
+
+def fill_random(t: torch.Tensor, seed: int, block0: int = 0):
+    """Counter-based synthetic payload (Threefry key {2, seed}); t must be a CUDA byte tensor."""
+    lib = _lib.load()
+    _lib.check(lib.ldpc_fill_random(_ptr(t), t.numel() * t.element_size(), seed & 0xFFFFFFFF, block0,
+                                    t.device.index or 0, _stream()))
+    return t
+
+
+def unpack_mask(mask, n):
+    """[B][mask_words] int32 bit mask -> [B][n] uint8 flags (numpy)."""
+    m = np.ascontiguousarray(mask.cpu().numpy() if hasattr(mask, "cpu") else mask).view(np.uint32)
+    bits = np.unpackbits(m.view(np.uint8), axis=1, bitorder="little")
+    return bits[:, :n].copy()
+
+
+def pack_mask(flags):
+    """[B][n] uint8 flags -> [B][ceil(n/32)] int32 bit mask (numpy)."""
+    B, n = flags.shape
+    nw = (n + 31) // 32
+    pad = np.zeros((B, nw * 32), np.uint8)
+    pad[:, :n] = flags
+    return np.packbits(pad, axis=1, bitorder="little").view(np.uint32).astype(np.int32, copy=False).reshape(B, nw)

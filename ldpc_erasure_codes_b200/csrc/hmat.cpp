@@ -1,0 +1,301 @@
+// hmat.cpp -- MAT-v5 reader + code-model builder (see hmat.hpp).
+#include "hmat.hpp"
+
+#include <zlib.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/ldpc_cuda.h"
+
+namespace ldpc {
+namespace {
+
+enum { miINT8 = 1, miUINT8 = 2, miINT16 = 3, miUINT16 = 4, miINT32 = 5, miUINT32 = 6, miSINGLE = 7,
+       miDOUBLE = 9, miINT64 = 12, miUINT64 = 13, miMATRIX = 14, miCOMPRESSED = 15 };
+
+struct Elem {
+    uint32_t type = 0;
+    uint32_t nbytes = 0;
+    const uint8_t *data = nullptr;
+    size_t total = 0;  // bytes consumed including tag and padding
+};
+
+uint32_t rd32(const uint8_t *p)
+{
+    uint32_t v;
+    memcpy(&v, p, 4);
+    return v;
+}
+
+// Parses one data element tag at p (avail bytes left).  Handles the "small data element"
+// packing (type in the low half-word, byte count in the high half-word, data in the tag).
+bool parse_elem(const uint8_t *p, size_t avail, Elem &e)
+{
+    if (avail < 8) return false;
+    uint32_t w0 = rd32(p);
+    if (w0 >> 16) {
+        e.type = w0 & 0xFFFFu;
+        e.nbytes = w0 >> 16;
+        if (e.nbytes > 4) return false;
+        e.data = p + 4;
+        e.total = 8;
+        return true;
+    }
+    e.type = w0;
+    e.nbytes = rd32(p + 4);
+    e.data = p + 8;
+    size_t padded = (e.type == miCOMPRESSED) ? e.nbytes : ((size_t(e.nbytes) + 7) & ~size_t(7));
+    if (8 + size_t(e.nbytes) > avail) return false;
+    e.total = std::min(avail, 8 + padded);
+    return true;
+}
+
+size_t type_size(uint32_t t)
+{
+    switch (t) {
+        case miINT8: case miUINT8: return 1;
+        case miINT16: case miUINT16: return 2;
+        case miINT32: case miUINT32: case miSINGLE: return 4;
+        case miDOUBLE: case miINT64: case miUINT64: return 8;
+        default: return 0;
+    }
+}
+
+bool numeric_at(const Elem &e, size_t i, double &v)
+{
+    const uint8_t *p = e.data + i * type_size(e.type);
+    switch (e.type) {
+        case miINT8: v = *reinterpret_cast<const int8_t *>(p); return true;
+        case miUINT8: v = *p; return true;
+        case miINT16: { int16_t x; memcpy(&x, p, 2); v = x; return true; }
+        case miUINT16: { uint16_t x; memcpy(&x, p, 2); v = x; return true; }
+        case miINT32: { int32_t x; memcpy(&x, p, 4); v = x; return true; }
+        case miUINT32: { uint32_t x; memcpy(&x, p, 4); v = x; return true; }
+        case miSINGLE: { float x; memcpy(&x, p, 4); v = x; return true; }
+        case miDOUBLE: { double x; memcpy(&x, p, 8); v = x; return true; }
+        case miINT64: { int64_t x; memcpy(&x, p, 8); v = double(x); return true; }
+        case miUINT64: { uint64_t x; memcpy(&x, p, 8); v = double(x); return true; }
+        default: return false;
+    }
+}
+
+bool inflate_all(const uint8_t *src, size_t n, std::vector<uint8_t> &out)
+{
+    z_stream zs;
+    memset(&zs, 0, sizeof(zs));
+    if (inflateInit(&zs) != Z_OK) return false;
+    zs.next_in = const_cast<Bytef *>(src);
+    zs.avail_in = static_cast<uInt>(n);
+    out.resize(std::max<size_t>(n * 8, 4096));
+    size_t have = 0;
+    int rc;
+    do {
+        if (have == out.size()) out.resize(out.size() * 2);
+        zs.next_out = out.data() + have;
+        zs.avail_out = static_cast<uInt>(out.size() - have);
+        rc = inflate(&zs, Z_NO_FLUSH);
+        have = out.size() - zs.avail_out;
+    } while (rc == Z_OK);
+    inflateEnd(&zs);
+    if (rc != Z_STREAM_END) return false;
+    out.resize(have);
+    return true;
+}
+
+// Parses one miMATRIX body.  On a name match fills the CSC arrays and returns 1; returns 0
+// if the variable is another one, <0 on a format error.
+int parse_matrix(const uint8_t *p, size_t n, const char *var_name, int &rows, int &cols,
+                 std::vector<int32_t> &col_ptr, std::vector<int32_t> &row_idx, std::string &err)
+{
+    size_t off = 0;
+    Elem flags, dims, name;
+    if (!parse_elem(p + off, n - off, flags) || flags.nbytes < 8) { err = "bad array-flags element"; return LDPC_ERR_FORMAT; }
+    off += flags.total;
+    if (!parse_elem(p + off, n - off, dims) || dims.type != miINT32 || dims.nbytes < 8) { err = "bad dimensions element"; return LDPC_ERR_FORMAT; }
+    off += dims.total;
+    if (!parse_elem(p + off, n - off, name)) { err = "bad name element"; return LDPC_ERR_FORMAT; }
+    off += name.total;
+    std::string nm(reinterpret_cast<const char *>(name.data), name.nbytes);
+    if (var_name && nm != var_name) return 0;
+    const uint32_t cls = rd32(flags.data) & 0xFFu;
+    if (dims.nbytes != 8) { err = "variable '" + nm + "' is not 2-D"; return LDPC_ERR_FORMAT; }
+    int32_t d0, d1;
+    memcpy(&d0, dims.data, 4);
+    memcpy(&d1, dims.data + 4, 4);
+    if (d0 <= 0 || d1 <= 0) { err = "empty matrix"; return LDPC_ERR_FORMAT; }
+    rows = d0;
+    cols = d1;
+    if (cls == 5) {  // mxSPARSE_CLASS: ir, jc, pr
+        Elem ir, jc, pr;
+        if (!parse_elem(p + off, n - off, ir)) { err = "missing ir"; return LDPC_ERR_FORMAT; }
+        off += ir.total;
+        if (!parse_elem(p + off, n - off, jc)) { err = "missing jc"; return LDPC_ERR_FORMAT; }
+        off += jc.total;
+        if (!parse_elem(p + off, n - off, pr)) { err = "missing pr"; return LDPC_ERR_FORMAT; }
+        const size_t sz_ir = type_size(ir.type), sz_jc = type_size(jc.type), sz_pr = type_size(pr.type);
+        if (!sz_ir || !sz_jc || !sz_pr) { err = "non-numeric sparse arrays"; return LDPC_ERR_FORMAT; }
+        const size_t n_jc = jc.nbytes / sz_jc;
+        if (n_jc != size_t(cols) + 1) { err = "jc length != columns + 1"; return LDPC_ERR_FORMAT; }
+        col_ptr.resize(n_jc);
+        for (size_t i = 0; i < n_jc; i++) { double v; numeric_at(jc, i, v); col_ptr[i] = int32_t(v); }
+        const size_t nnz = size_t(col_ptr[cols]);
+        if (col_ptr[0] != 0 || ir.nbytes / sz_ir < nnz || pr.nbytes / sz_pr < nnz) { err = "inconsistent ir/jc/pr sizes"; return LDPC_ERR_FORMAT; }
+        row_idx.clear();
+        std::vector<int32_t> cp(cols + 1, 0);
+        for (int c = 0; c < cols; c++) {
+            if (col_ptr[c + 1] < col_ptr[c]) { err = "jc not monotone"; return LDPC_ERR_FORMAT; }
+            for (int32_t j = col_ptr[c]; j < col_ptr[c + 1]; j++) {
+                double r, v;
+                numeric_at(ir, size_t(j), r);
+                numeric_at(pr, size_t(j), v);
+                if (r < 0 || r >= rows) { err = "row index out of range"; return LDPC_ERR_FORMAT; }
+                const long iv = long(v);
+                if (double(iv) != v) { err = "H entry is not an integer"; return LDPC_ERR_FORMAT; }
+                if (iv & 1) row_idx.push_back(int32_t(r));  // entries are taken mod 2
+            }
+            cp[c + 1] = int32_t(row_idx.size());
+        }
+        col_ptr = cp;
+        return 1;
+    }
+    if (cls >= 6 && cls <= 15) {  // full numeric matrix, column-major
+        Elem pr;
+        if (!parse_elem(p + off, n - off, pr)) { err = "missing pr"; return LDPC_ERR_FORMAT; }
+        const size_t sz = type_size(pr.type);
+        if (!sz || pr.nbytes / sz < size_t(rows) * size_t(cols)) { err = "full matrix data too short"; return LDPC_ERR_FORMAT; }
+        col_ptr.assign(cols + 1, 0);
+        row_idx.clear();
+        for (int c = 0; c < cols; c++) {
+            for (int r = 0; r < rows; r++) {
+                double v;
+                numeric_at(pr, size_t(c) * rows + r, v);
+                if (long(v) & 1) row_idx.push_back(r);
+            }
+            col_ptr[c + 1] = int32_t(row_idx.size());
+        }
+        return 1;
+    }
+    err = "variable '" + nm + "' has unsupported class " + std::to_string(cls);
+    return LDPC_ERR_FORMAT;
+}
+
+}  // namespace
+
+int load_mat_sparse(const std::string &path, const char *var_name, int &rows, int &cols,
+                    std::vector<int32_t> &col_ptr, std::vector<int32_t> &row_idx, std::string &err)
+{
+    FILE *f = fopen(path.c_str(), "rb");
+    if (!f) { err = "cannot open " + path; return LDPC_ERR_IO; }
+    std::vector<uint8_t> buf;
+    uint8_t tmp[65536];
+    size_t got;
+    while ((got = fread(tmp, 1, sizeof(tmp), f)) > 0) buf.insert(buf.end(), tmp, tmp + got);
+    fclose(f);
+    if (buf.size() < 136) { err = path + ": too short for a MAT-v5 file"; return LDPC_ERR_FORMAT; }
+    if (memcmp(buf.data(), "MATLAB 5.0 MAT-file", 19) != 0) { err = path + ": not a MAT-v5 file"; return LDPC_ERR_FORMAT; }
+    if (!(buf[126] == 'I' && buf[127] == 'M')) { err = path + ": big-endian MAT files are not supported"; return LDPC_ERR_FORMAT; }
+    size_t off = 128;
+    while (off + 8 <= buf.size()) {
+        Elem e;
+        if (!parse_elem(buf.data() + off, buf.size() - off, e)) { err = path + ": truncated data element"; return LDPC_ERR_FORMAT; }
+        const uint8_t *body = e.data;
+        size_t body_n = e.nbytes;
+        std::vector<uint8_t> inflated;
+        uint32_t type = e.type;
+        if (type == miCOMPRESSED) {
+            if (!inflate_all(e.data, e.nbytes, inflated)) { err = path + ": zlib inflate failed"; return LDPC_ERR_FORMAT; }
+            Elem inner;
+            if (!parse_elem(inflated.data(), inflated.size(), inner)) { err = path + ": bad compressed element"; return LDPC_ERR_FORMAT; }
+            type = inner.type;
+            body = inner.data;
+            body_n = inner.nbytes;
+        }
+        if (type == miMATRIX) {
+            int rc = parse_matrix(body, body_n, var_name, rows, cols, col_ptr, row_idx, err);
+            if (rc < 0) { err = path + ": " + err; return rc; }
+            if (rc == 1) return LDPC_OK;
+        }
+        off += e.total;
+    }
+    err = path + ": variable '" + std::string(var_name ? var_name : "?") + "' not found";
+    return LDPC_ERR_FORMAT;
+}
+
+int build_code(int rows, int cols, const std::vector<int32_t> &col_ptr,
+               const std::vector<int32_t> &row_idx, HostCode &code, std::string &err)
+{
+    code = HostCode();
+    code.m = rows;
+    code.n = cols;
+    code.k = cols - rows;
+    code.nnz = int(row_idx.size());
+    if (code.k <= 0) { err = "H must have more columns than rows"; return LDPC_ERR_FORMAT; }
+    code.col_ptr = col_ptr;
+    code.row_idx = row_idx;
+    // CSC -> CSR (columns visited ascending, so each row comes out ascending)
+    code.row_ptr.assign(rows + 1, 0);
+    for (int32_t r : row_idx) code.row_ptr[r + 1]++;
+    for (int r = 0; r < rows; r++) code.row_ptr[r + 1] += code.row_ptr[r];
+    code.col_idx.resize(row_idx.size());
+    std::vector<int32_t> fill(code.row_ptr.begin(), code.row_ptr.end() - 1);
+    for (int c = 0; c < cols; c++) {
+        for (int32_t j = col_ptr[c]; j < col_ptr[c + 1]; j++) {
+            if (j > col_ptr[c] && row_idx[j] <= row_idx[j - 1]) { err = "row indices not ascending inside a column"; return LDPC_ERR_FORMAT; }
+            code.col_idx[fill[row_idx[j]]++] = c;
+        }
+        code.max_col_weight = std::max(code.max_col_weight, col_ptr[c + 1] - col_ptr[c]);
+    }
+    code.triangular = true;
+    for (int r = 0; r < rows; r++) {
+        const int w = code.row_ptr[r + 1] - code.row_ptr[r];
+        code.max_row_weight = std::max(code.max_row_weight, w);
+        if (w == 0 || code.col_idx[code.row_ptr[r + 1] - 1] != code.k + r) code.triangular = false;
+    }
+    if (code.n > 65534 || code.m > 2047 || code.max_row_weight > 31) {
+        err = "code outside kernel limits (n <= 65534, m <= 2047, row weight <= 31)";
+        return LDPC_ERR_UNSUPPORTED;
+    }
+    code.RW = (code.max_row_weight + 7) & ~7;
+    code.VW = code.max_col_weight <= 4 ? 4 : ((code.max_col_weight + 7) & ~7);
+    code.cidx.assign(size_t(rows) * code.RW, 0xFFFFu);
+    for (int r = 0; r < rows; r++)
+        for (int j = code.row_ptr[r]; j < code.row_ptr[r + 1]; j++)
+            code.cidx[size_t(r) * code.RW + (j - code.row_ptr[r])] = uint16_t(code.col_idx[j]);
+    code.vadj.assign(size_t(cols) * code.VW, 0xFFFFu);
+    for (int c = 0; c < cols; c++)
+        for (int j = col_ptr[c]; j < col_ptr[c + 1]; j++)
+            code.vadj[size_t(c) * code.VW + (j - col_ptr[c])] = uint16_t(row_idx[j]);
+
+    // Encoder level schedule: parity r = XOR of the row's members except its last one (the
+    // diagonal), so row r depends on the rows whose parity it references.
+    if (code.triangular) {
+        std::vector<int> level(rows, 1);
+        int nl = 0;
+        for (int r = 0; r < rows; r++) {
+            int l = 0;
+            for (int j = code.row_ptr[r]; j < code.row_ptr[r + 1] - 1; j++) {
+                const int c = code.col_idx[j];
+                if (c >= code.k) l = std::max(l, level[c - code.k]);
+            }
+            level[r] = l + 1;
+            nl = std::max(nl, level[r]);
+        }
+        code.encode_levels = nl;
+        std::vector<uint16_t> lvl_off(nl + 1, 0);
+        for (int r = 0; r < rows; r++) lvl_off[level[r]]++;
+        for (int l = 1; l <= nl; l++) lvl_off[l] = uint16_t(lvl_off[l] + lvl_off[l - 1]);
+        std::vector<uint32_t> entries(rows);
+        std::vector<uint16_t> pos(lvl_off.begin(), lvl_off.end());
+        for (int r = 0; r < rows; r++) entries[pos[level[r] - 1]++] = uint32_t(code.k + r) | (uint32_t(r) << 16);
+        code.enc_blob.assign(size_t(sched_blob_max_bytes(rows)), 0);
+        uint32_t hdr[4] = {uint32_t(rows), uint32_t(nl), 0u, 0u};
+        memcpy(code.enc_blob.data(), hdr, 16);
+        memcpy(code.enc_blob.data() + 16, entries.data(), size_t(rows) * 4);
+        memcpy(code.enc_blob.data() + 16 + size_t(rows) * 4, lvl_off.data(), size_t(nl + 1) * 2);
+    }
+    return LDPC_OK;
+}
+
+}  // namespace ldpc

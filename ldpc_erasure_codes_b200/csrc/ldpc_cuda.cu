@@ -1,0 +1,641 @@
+// ldpc_cuda.cu -- C ABI of libldpc_cuda (see include/ldpc_cuda.h) and the host runtime that
+// stands where the reference's OpenCL host (OpenCL/host/src/main.cpp) stands: context
+// creation (init_opencl :439-544), kernel launches (run :555-659), counters (data_out),
+// teardown (cleanup :668-691).
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/ldpc_cuda.h"
+#include "erasure_gen.cuh"
+#include "hmat.hpp"
+#include "hybrid_ge.cuh"
+#include "payload_exec.cuh"
+#include "peel_schedule.cuh"
+#include "rs_gf256.cuh"
+
+using namespace ldpc;
+
+// ------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------
+static thread_local std::string g_err = "";
+
+static int fail(int code, const std::string &msg)
+{
+    g_err = msg;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                       \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess)                                                               \
+            return fail(LDPC_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));  \
+    } while (0)
+
+// LDPC_CUDA_DEBUG_SYNC=1: synchronise after every launch so that a faulting kernel is named
+static int debug_sync(const char *what, cudaStream_t st)
+{
+    static int on = -1;
+    if (on < 0) { const char *e = getenv("LDPC_CUDA_DEBUG_SYNC"); on = (e && *e && *e != '0') ? 1 : 0; }
+    if (!on) return LDPC_OK;
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return fail(LDPC_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+    fprintf(stderr, "[ldpc_cuda] %s ok\n", what);
+    return LDPC_OK;
+}
+
+extern "C" const char *ldpc_last_error_string(void) { return g_err.c_str(); }
+extern "C" int ldpc_cuda_abi_version(void) { return LDPC_CUDA_ABI_VERSION; }
+
+// ------------------------------------------------------------------------------------------
+// driver entry point for tensor-map encoding (libcuda is not linked; resolved at run time)
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                    CUtensorMapFloatOOBfill);
+
+static int get_encode_fn(PFN_encodeTiled *fn)
+{
+    static PFN_encodeTiled cached = nullptr;
+    if (!cached) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+        if (!p || q != cudaDriverEntryPointSuccess) return fail(LDPC_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+        cached = reinterpret_cast<PFN_encodeTiled>(p);
+    }
+    *fn = cached;
+    return LDPC_OK;
+}
+
+// 3-D byte tensor [B][rows][S], box {W, 256, 1}
+static int make_map(CUtensorMap *map, const void *base, int S, int rows, long long B, int W, bool is_load)
+{
+    PFN_encodeTiled enc;
+    int rc = get_encode_fn(&enc);
+    if (rc) return rc;
+    cuuint64_t dims[3] = {cuuint64_t(S), cuuint64_t(rows), cuuint64_t(B)};
+    cuuint64_t strides[2] = {cuuint64_t(S), cuuint64_t(S) * cuuint64_t(rows)};
+    cuuint32_t box[3] = {cuuint32_t(W), cuuint32_t(kBoxRows), 1u};
+    cuuint32_t estr[3] = {1u, 1u, 1u};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void *>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                     is_load ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(LDPC_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string(int(r)));
+    return LDPC_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------
+struct ExecGeom {
+    int W = 0, nslot = 0, slot_bytes = 0, smem_bytes = 0, sched_area = 0;
+};
+
+struct ldpc_ctx {
+    HostCode code;
+    int S = 0, device = 0, code_ind = -1;
+    int rs_n = 0, rs_k = 0;
+    long long max_batch = 0;
+    int num_sms = 0, smem_optin = 0;
+    int NW = 0, MW = 0, sched_stride = 0;
+    // device tables
+    uint16_t *d_cidx = nullptr, *d_vadj = nullptr;
+    uint8_t *d_enc_blob = nullptr;
+    // scratch
+    uint8_t *d_sched = nullptr;
+    uint32_t *d_sched_len = nullptr;
+    uint32_t *d_resid = nullptr;
+    uint8_t *d_fail_scratch = nullptr;
+    unsigned long long *d_stats = nullptr;
+    // geometry
+    ExecGeom dec, enc;
+    int force_W = 0, force_slots = 0;
+    int peel_G = 8, peel_groups = 0, peel_smem = 0;
+    // hybrid stage
+    HybridScratch hyb;
+    // host-buffer pipeline
+    cudaStream_t hstream[2] = {nullptr, nullptr};
+    uint8_t *h_in[2] = {nullptr, nullptr}, *h_out[2] = {nullptr, nullptr};
+    uint32_t *h_mask[2] = {nullptr, nullptr};
+    uint8_t *h_fail[2] = {nullptr, nullptr};
+    long long host_chunk = 0;
+};
+
+static const struct { const char *name; int n, k, rs_n, rs_k; } kBuiltin[] = {
+    // OpenCL/device/LDPC_Vlist_data.h:10-14 (ldpc_params) + the .mat-only (4000,2000) code
+    {"n2000_k1000", 2000, 1000, 250, 125},
+    {"n2040_k1530", 2040, 1530, 255, 192},
+    {"n4000_k2000", 4000, 2000, 250, 125},
+};
+
+static std::string codes_dir()
+{
+    if (const char *e = getenv("LDPC_CUDA_CODES_DIR")) return e;
+    Dl_info info;
+    if (dladdr(reinterpret_cast<void *>(&ldpc_cuda_abi_version), &info) && info.dli_fname) {
+        std::string p = info.dli_fname;
+        size_t s = p.find_last_of('/');
+        return (s == std::string::npos ? std::string(".") : p.substr(0, s)) + "/codes";
+    }
+    return "codes";
+}
+
+static int choose_geom(const ldpc_ctx *c, bool dynamic_sched, ExecGeom *g)
+{
+    const int n = c->code.n, S = c->S;
+    const int cidx_bytes = c->code.m * c->code.RW * 2;
+    const int blob = sched_blob_max_bytes(c->code.m);
+    const int fixed = cidx_bytes + 2 * 8 * 8 + 256;
+    ExecGeom best;
+    for (int W = std::min(S, 64); W >= 16; W >>= 1) {
+        if (S % W) continue;
+        if (c->force_W && W != c->force_W) continue;
+        const int slot = ((n + kBoxRows - 1) / kBoxRows) * kBoxRows * W;
+        int nslot;
+        if (dynamic_sched) nslot = (c->smem_optin - fixed) / (slot + blob);
+        else nslot = (c->smem_optin - fixed - blob) / slot;
+        nslot = std::min(nslot, 4);
+        if (c->force_slots) nslot = std::min(nslot, c->force_slots);
+        if (nslot < 1) continue;
+        ExecGeom cand;
+        cand.W = W; cand.nslot = nslot; cand.slot_bytes = slot; cand.sched_area = blob;
+        cand.smem_bytes = nslot * slot + (dynamic_sched ? nslot : 1) * blob + cidx_bytes + 2 * 8 * 8;
+        if (!best.W || (best.nslot < 3 && cand.nslot > best.nslot)) best = cand;
+        if (best.nslot >= 3) break;
+    }
+    if (!best.W) return fail(LDPC_ERR_UNSUPPORTED, "code too long for one shared-memory slot (n * 16 bytes must fit)");
+    *g = best;
+    return LDPC_OK;
+}
+
+static void free_ctx(ldpc_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaFree(c->d_cidx); cudaFree(c->d_vadj); cudaFree(c->d_enc_blob); cudaFree(c->d_sched);
+    cudaFree(c->d_sched_len); cudaFree(c->d_resid); cudaFree(c->d_stats); cudaFree(c->d_fail_scratch);
+    hybrid_free(c->hyb);
+    for (int i = 0; i < 2; i++) {
+        if (c->hstream[i]) cudaStreamDestroy(c->hstream[i]);
+        cudaFree(c->h_in[i]); cudaFree(c->h_out[i]); cudaFree(c->h_mask[i]); cudaFree(c->h_fail[i]);
+    }
+    delete c;
+}
+
+static int setup_peel(ldpc_ctx *c)
+{
+    const int tables = c->code.n * c->code.VW * 2 + c->code.m * c->code.RW * 2;
+    const int per_group = peel_group_words(c->code.m, c->MW, c->NW) * 4;
+    const int G = 8;
+    int groups = (c->smem_optin - 64 - tables) / per_group;
+    groups = std::min(groups, 1024 / G);
+    groups = (groups / (32 / G)) * (32 / G);
+    if (groups < 32 / G) return fail(LDPC_ERR_UNSUPPORTED, "code too large for the peel kernel's shared memory");
+    c->peel_G = G;
+    c->peel_groups = groups;
+    c->peel_smem = tables + groups * per_group;
+    CUDA_TRY(cudaFuncSetAttribute(peel_schedule_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->peel_smem));
+    return LDPC_OK;
+}
+
+extern "C" int ldpc_ctx_create(ldpc_ctx **out, const char *h_mat_path, int code_ind, int symbol_bytes, int device,
+                               int64_t max_batch)
+{
+    if (!out) return fail(LDPC_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    if (symbol_bytes <= 0 || symbol_bytes % 16) return fail(LDPC_ERR_ARG, "symbol_bytes must be a positive multiple of 16");
+    if (max_batch <= 0) return fail(LDPC_ERR_ARG, "max_batch must be positive");
+    std::string path;
+    int rs_n = 0, rs_k = 0;
+    if (h_mat_path && *h_mat_path) {
+        path = h_mat_path;
+    } else {
+        if (code_ind < 0 || code_ind >= int(sizeof(kBuiltin) / sizeof(kBuiltin[0])))
+            return fail(LDPC_ERR_ARG, "code_ind out of range (0 = (2000,1000), 1 = (2040,1530), 2 = (4000,2000))");
+        path = codes_dir() + "/" + kBuiltin[code_ind].name + ".mat";
+        rs_n = kBuiltin[code_ind].rs_n;
+        rs_k = kBuiltin[code_ind].rs_k;
+    }
+    int rows, cols;
+    std::vector<int32_t> col_ptr, row_idx;
+    std::string err;
+    int rc = load_mat_sparse(path, "H_sparse", rows, cols, col_ptr, row_idx, err);
+    if (rc) return fail(rc, err);
+    ldpc_ctx *c = new (std::nothrow) ldpc_ctx();
+    if (!c) return fail(LDPC_ERR_NOMEM, "out of host memory");
+    rc = build_code(rows, cols, col_ptr, row_idx, c->code, err);
+    if (rc) { delete c; return fail(rc, err); }
+    if (!(h_mat_path && *h_mat_path) && (c->code.n != kBuiltin[code_ind].n || c->code.k != kBuiltin[code_ind].k)) {
+        delete c;
+        return fail(LDPC_ERR_FORMAT, path + ": dimensions do not match the built-in code table");
+    }
+    if (rs_n == 0) {  // RS-equivalent for a user code: blocks of <= 255 at the same rate (SURVEY a-2)
+        for (int blk = 255; blk >= 16; blk--)
+            if (c->code.n % blk == 0) { rs_n = blk; rs_k = int(std::ceil(double(blk) * c->code.k / c->code.n)); break; }
+    }
+    c->S = symbol_bytes; c->device = device; c->code_ind = (h_mat_path && *h_mat_path) ? -1 : code_ind;
+    c->rs_n = rs_n; c->rs_k = rs_k; c->max_batch = max_batch;
+    c->NW = (c->code.n + 31) / 32; c->MW = (c->code.m + 31) / 32;
+    c->sched_stride = sched_blob_max_bytes(c->code.m);
+
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) { delete c; return fail(LDPC_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e)); }
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) { delete c; return fail(LDPC_ERR_CUDA, std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e)); }
+    if (prop.major != 10) {
+        delete c;
+        return fail(LDPC_ERR_UNSUPPORTED, "libldpc_cuda is built for sm_100a (B200) only; device is sm_" +
+                                              std::to_string(prop.major) + std::to_string(prop.minor));
+    }
+    c->num_sms = prop.multiProcessorCount;
+    c->smem_optin = int(prop.sharedMemPerBlockOptin);
+
+#define CTX_TRY(expr)                                                                                   \
+    do {                                                                                                \
+        cudaError_t _e = (expr);                                                                        \
+        if (_e != cudaSuccess) {                                                                        \
+            free_ctx(c);                                                                                \
+            return fail(_e == cudaErrorMemoryAllocation ? LDPC_ERR_NOMEM : LDPC_ERR_CUDA,               \
+                        std::string(#expr) + ": " + cudaGetErrorString(_e));                            \
+        }                                                                                               \
+    } while (0)
+    CTX_TRY(cudaMalloc(&c->d_cidx, c->code.cidx.size() * 2));
+    CTX_TRY(cudaMemcpy(c->d_cidx, c->code.cidx.data(), c->code.cidx.size() * 2, cudaMemcpyHostToDevice));
+    CTX_TRY(cudaMalloc(&c->d_vadj, c->code.vadj.size() * 2));
+    CTX_TRY(cudaMemcpy(c->d_vadj, c->code.vadj.data(), c->code.vadj.size() * 2, cudaMemcpyHostToDevice));
+    if (c->code.triangular) {
+        CTX_TRY(cudaMalloc(&c->d_enc_blob, c->code.enc_blob.size()));
+        CTX_TRY(cudaMemcpy(c->d_enc_blob, c->code.enc_blob.data(), c->code.enc_blob.size(), cudaMemcpyHostToDevice));
+    }
+    CTX_TRY(cudaMalloc(&c->d_sched, size_t(max_batch) * c->sched_stride));
+    CTX_TRY(cudaMalloc(&c->d_sched_len, size_t(max_batch) * 4));
+    CTX_TRY(cudaMalloc(&c->d_resid, size_t(max_batch) * 4));
+    CTX_TRY(cudaMalloc(&c->d_fail_scratch, size_t(max_batch)));
+    CTX_TRY(cudaMalloc(&c->d_stats, 8 * sizeof(unsigned long long)));
+    CTX_TRY(cudaMemset(c->d_stats, 0, 8 * sizeof(unsigned long long)));
+#undef CTX_TRY
+    rc = choose_geom(c, true, &c->dec);
+    if (!rc) rc = choose_geom(c, false, &c->enc);
+    if (!rc) rc = setup_peel(c);
+    if (rc) { free_ctx(c); return rc; }
+    *out = c;
+    return LDPC_OK;
+}
+
+extern "C" int ldpc_ctx_destroy(ldpc_ctx *ctx)
+{
+    free_ctx(ctx);
+    return LDPC_OK;
+}
+
+extern "C" int ldpc_ctx_info(const ldpc_ctx *c, ldpc_code_info *info)
+{
+    if (!c || !info) return fail(LDPC_ERR_ARG, "NULL argument");
+    info->n = c->code.n; info->k = c->code.k; info->m = c->code.m; info->nnz = c->code.nnz;
+    info->symbol_bytes = c->S; info->mask_words = c->NW; info->rs_n = c->rs_n; info->rs_k = c->rs_k;
+    info->max_row_weight = c->code.max_row_weight; info->max_col_weight = c->code.max_col_weight;
+    info->encode_levels = c->code.encode_levels; info->slice_bytes = c->dec.W; info->exec_slots = c->dec.nslot;
+    info->device = c->device; info->max_batch = c->max_batch;
+    return LDPC_OK;
+}
+
+extern "C" int ldpc_ctx_get_csr(const ldpc_ctx *c, int32_t *row_ptr, int32_t *col_idx)
+{
+    if (!c) return fail(LDPC_ERR_ARG, "NULL context");
+    if (row_ptr) memcpy(row_ptr, c->code.row_ptr.data(), c->code.row_ptr.size() * 4);
+    if (col_idx) memcpy(col_idx, c->code.col_idx.data(), c->code.col_idx.size() * 4);
+    return LDPC_OK;
+}
+
+extern "C" int ldpc_ctx_set_exec_geometry(ldpc_ctx *c, int slice_bytes, int slots)
+{
+    if (!c) return fail(LDPC_ERR_ARG, "NULL context");
+    if (slice_bytes && (slice_bytes % 16 || c->S % slice_bytes || slice_bytes > 64))
+        return fail(LDPC_ERR_ARG, "slice_bytes must be 16, 32 or 64 and divide symbol_bytes");
+    const int oldW = c->force_W, olds = c->force_slots;
+    c->force_W = slice_bytes; c->force_slots = slots;
+    ExecGeom d, e;
+    int rc = choose_geom(c, true, &d);
+    if (!rc) rc = choose_geom(c, false, &e);
+    if (rc) { c->force_W = oldW; c->force_slots = olds; return rc; }
+    c->dec = d; c->enc = e;
+    return LDPC_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// executor launch
+// ------------------------------------------------------------------------------------------
+typedef void (*ExecKernel)(const CUtensorMap, const CUtensorMap, const ExecParams);
+
+static ExecKernel pick_exec(int W, int RWQ)
+{
+    switch (W * 8 + RWQ) {
+        case 16 * 8 + 1: return payload_exec_kernel<16, 1>;
+        case 16 * 8 + 2: return payload_exec_kernel<16, 2>;
+        case 16 * 8 + 3: return payload_exec_kernel<16, 3>;
+        case 16 * 8 + 4: return payload_exec_kernel<16, 4>;
+        case 32 * 8 + 1: return payload_exec_kernel<32, 1>;
+        case 32 * 8 + 2: return payload_exec_kernel<32, 2>;
+        case 32 * 8 + 3: return payload_exec_kernel<32, 3>;
+        case 32 * 8 + 4: return payload_exec_kernel<32, 4>;
+        case 64 * 8 + 1: return payload_exec_kernel<64, 1>;
+        case 64 * 8 + 2: return payload_exec_kernel<64, 2>;
+        case 64 * 8 + 3: return payload_exec_kernel<64, 3>;
+        case 64 * 8 + 4: return payload_exec_kernel<64, 4>;
+        default: return nullptr;
+    }
+}
+
+static int launch_exec(ldpc_ctx *c, const ExecGeom &g, const void *d_in, int rows_in, void *d_out, int rows_out,
+                       const uint8_t *sched, const uint32_t *sched_len, int sched_stride, long long B,
+                       cudaStream_t st)
+{
+    if (B <= 0) return LDPC_OK;
+    CUtensorMap in_map, out_map;
+    int rc = make_map(&in_map, d_in, c->S, rows_in, B, g.W, true);
+    if (rc) return rc;
+    rc = make_map(&out_map, d_out, c->S, rows_out, B, g.W, false);
+    if (rc) return rc;
+    ExecParams p;
+    p.cidx = c->d_cidx; p.sched = sched; p.sched_len = sched_len; p.B = B; p.sched_stride = sched_stride;
+    p.sched_max = g.sched_area; p.m = c->code.m; p.RW = c->code.RW; p.rows_in = rows_in; p.rows_out = rows_out;
+    p.nbox_in = (rows_in + kBoxRows - 1) / kBoxRows; p.nbox_out = (rows_out + kBoxRows - 1) / kBoxRows;
+    p.slices = c->S / g.W; p.nslot = g.nslot; p.slot_bytes = g.slot_bytes;
+    ExecKernel k = pick_exec(g.W, c->code.RW / 8);
+    if (!k) return fail(LDPC_ERR_UNSUPPORTED, "no executor instantiation for this slice width / row weight");
+    CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem_bytes));
+    const int grid = int(std::min<long long>(c->num_sms, B));
+    k<<<grid, kExecThreads, g.smem_bytes, st>>>(in_map, out_map, p);
+    CUDA_TRY(cudaGetLastError());
+    return debug_sync(sched_stride ? "payload_exec_kernel(decode)" : "payload_exec_kernel(encode)", st);
+}
+
+// ------------------------------------------------------------------------------------------
+// encoder
+// ------------------------------------------------------------------------------------------
+extern "C" int ldpc_encode(ldpc_ctx *c, const void *d_info, void *d_cw, int64_t B, void *stream)
+{
+    if (!c || !d_info || !d_cw || B < 0) return fail(LDPC_ERR_ARG, "bad argument to ldpc_encode");
+    if (!c->code.triangular)
+        return fail(LDPC_ERR_NOT_TRIANGULAR, "H is not in triangular form (last entry of row r must be column k + r)");
+    CUDA_TRY(cudaSetDevice(c->device));
+    // the tensor map's batch dimension is 32-bit friendly; split very large batches
+    const long long step = 1ll << 22;
+    for (long long b0 = 0; b0 < B; b0 += step) {
+        const long long nb = std::min<long long>(step, B - b0);
+        int rc = launch_exec(c, c->enc, static_cast<const uint8_t *>(d_info) + size_t(b0) * c->code.k * c->S, c->code.k,
+                             static_cast<uint8_t *>(d_cw) + size_t(b0) * c->code.n * c->S, c->code.n, c->d_enc_blob,
+                             nullptr, 0, nb, static_cast<cudaStream_t>(stream));
+        if (rc) return rc;
+    }
+    return LDPC_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// erasure channel
+// ------------------------------------------------------------------------------------------
+static void prob_threshold(double prob, uint32_t *t, int *always, int *never)
+{
+    *always = prob >= 1.0;
+    *never = prob < 0.0;
+    *t = 0;
+    if (!*always && !*never) *t = uint32_t(std::floor(prob * 4294967296.0));  // v <= t  <=>  v / 2^32 <= prob
+}
+
+extern "C" int ldpc_gen_erasures(ldpc_ctx *c, const ldpc_erasure_model *model, uint32_t seed, uint64_t frame0,
+                                 int64_t B, uint32_t *d_mask, void *d_payload, void *stream)
+{
+    if (!c || !model || !d_mask || B < 0) return fail(LDPC_ERR_ARG, "bad argument to ldpc_gen_erasures");
+    if (B == 0) return LDPC_OK;
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    GenParams p;
+    memset(&p, 0, sizeof(p));
+    p.mask = d_mask; p.B = B; p.frame0 = frame0; p.seed = seed; p.n = c->code.n; p.NW = c->NW; p.model = model->model;
+    const int threads = 256;
+    if (model->model == LDPC_ERASURE_IID64 || model->model == LDPC_ERASURE_IID32) {
+        if (model->model == LDPC_ERASURE_IID64) {
+            if (model->per_numerator_div_64 < 0 || model->per_numerator_div_64 > 64)
+                return fail(LDPC_ERR_ARG, "per_numerator_div_64 must be in 0..64");
+            p.thr = uint32_t(model->per_numerator_div_64);
+        } else {
+            p.thr = model->threshold32;
+        }
+        const long long warps = B * c->NW;
+        const int grid = int(std::min<long long>((warps + 7) / 8, (long long)c->num_sms * 32));
+        gen_erasures_iid_kernel<<<grid, threads, 0, st>>>(p);
+    } else if (model->model == LDPC_ERASURE_BURSTY) {
+        if (!(model->bias > 0.0)) return fail(LDPC_ERR_ARG, "bursty model needs bias > 0");
+        const double p01 = 0.1 / model->bias, p10 = 0.1;  // Bursty_Error_Channel_Model_Generator.m:14-17
+        prob_threshold(model->alpha, &p.t_alpha, &p.a_alpha, &p.n_alpha);
+        prob_threshold(model->beta, &p.t_beta, &p.a_beta, &p.n_beta);
+        prob_threshold(p01, &p.t_p01, &p.a_p01, &p.n_p01);
+        prob_threshold(p10, &p.t_p10, &p.a_p10, &p.n_p10);
+        if (p.t_p01 == p.t_p10 && p.a_p01 == p.a_p10)
+            return fail(LDPC_ERR_UNSUPPORTED, "bursty model with bias == 1 has no resynchronising symbols");
+        const int grid = int(std::min<long long>((B + 7) / 8, (long long)c->num_sms * 32));
+        gen_erasures_bursty_kernel<<<grid, threads, 0, st>>>(p);
+    } else {
+        return fail(LDPC_ERR_ARG, "unknown erasure model");
+    }
+    CUDA_TRY(cudaGetLastError());
+    if (d_payload) {
+        const long long warps = B * c->NW;
+        const int grid = int(std::min<long long>((warps + 7) / 8, (long long)c->num_sms * 32));
+        zero_erased_kernel<<<grid, threads, 0, st>>>(d_mask, static_cast<uint8_t *>(d_payload), B, c->code.n, c->NW, c->S);
+        CUDA_TRY(cudaGetLastError());
+    }
+    return LDPC_OK;
+}
+
+extern "C" int ldpc_fill_random(void *d_dst, int64_t nbytes, uint32_t seed, uint64_t block0, int device, void *stream)
+{
+    if (!d_dst || nbytes < 0 || nbytes % 16) return fail(LDPC_ERR_ARG, "ldpc_fill_random: nbytes must be a multiple of 16");
+    if (nbytes == 0) return LDPC_OK;
+    CUDA_TRY(cudaSetDevice(device));
+    const long long nblocks = nbytes / 16;
+    const int grid = int(std::min<long long>((nblocks + 255) / 256, 148 * 16));
+    fill_random_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<uint4 *>(d_dst), nblocks, seed, block0);
+    CUDA_TRY(cudaGetLastError());
+    return LDPC_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// decoder
+// ------------------------------------------------------------------------------------------
+static int decode_chunk(ldpc_ctx *c, const uint8_t *d_cw, const uint32_t *d_mask, uint8_t *d_out, uint8_t *d_fail,
+                        int max_iter, int mode, long long B, cudaStream_t st)
+{
+    PeelParams pp;
+    pp.mask = d_mask; pp.sched = c->d_sched; pp.sched_len = c->d_sched_len;
+    pp.fail = d_fail ? d_fail : c->d_fail_scratch; pp.resid = c->d_resid; pp.stats = c->d_stats;
+    pp.cidx = c->d_cidx; pp.vadj = c->d_vadj; pp.B = B; pp.n = c->code.n; pp.k = c->code.k; pp.m = c->code.m;
+    pp.RW = c->code.RW; pp.VW = c->code.VW; pp.NW = c->NW; pp.MW = c->MW; pp.stride = c->sched_stride;
+    pp.max_iter = max_iter; pp.rs_n = c->rs_n; pp.rs_k = c->rs_k; pp.groups_per_block = c->peel_groups;
+    pp.count_stats = 1;
+    const int grid = int(std::min<long long>(c->num_sms, (B + c->peel_groups - 1) / c->peel_groups));
+    peel_schedule_kernel<8><<<grid, c->peel_groups * c->peel_G, c->peel_smem, st>>>(pp);
+    CUDA_TRY(cudaGetLastError());
+    { int rcd = debug_sync("peel_schedule_kernel", st); if (rcd) return rcd; }
+    int rc = launch_exec(c, c->dec, d_cw, c->code.n, d_out, c->code.k, c->d_sched, c->d_sched_len, c->sched_stride, B, st);
+    if (rc) return rc;
+    if (mode == LDPC_MODE_HYBRID) {
+        rc = hybrid_stage(c->hyb, c->code, c->d_cidx, c->S, c->num_sms, c->smem_optin, d_cw, d_mask, c->d_sched,
+                          c->sched_stride, c->d_resid, d_out, pp.fail, c->d_stats, B, c->max_batch, st, g_err);
+        if (rc) return rc;
+    }
+    return LDPC_OK;
+}
+
+extern "C" int ldpc_decode(ldpc_ctx *c, const void *d_cw, const uint32_t *d_mask, void *d_out, uint8_t *d_fail,
+                           int max_iter, int mode, int64_t B, void *stream)
+{
+    if (!c || !d_cw || !d_mask || !d_out || B < 0) return fail(LDPC_ERR_ARG, "bad argument to ldpc_decode");
+    if (mode != LDPC_MODE_PEEL && mode != LDPC_MODE_HYBRID) return fail(LDPC_ERR_ARG, "unknown decode mode");
+    if (max_iter < 0 || max_iter > 1000000) return fail(LDPC_ERR_ARG, "max_iter out of range");
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    for (long long b0 = 0; b0 < B; b0 += c->max_batch) {
+        const long long nb = std::min<long long>(c->max_batch, B - b0);
+        int rc = decode_chunk(c, static_cast<const uint8_t *>(d_cw) + size_t(b0) * c->code.n * c->S,
+                              d_mask + size_t(b0) * c->NW, static_cast<uint8_t *>(d_out) + size_t(b0) * c->code.k * c->S,
+                              d_fail ? d_fail + b0 : nullptr, max_iter, mode, nb, st);
+        if (rc) return rc;
+    }
+    return LDPC_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// statistics
+// ------------------------------------------------------------------------------------------
+extern "C" int ldpc_get_stats(ldpc_ctx *c, ldpc_stats *out)
+{
+    if (!c || !out) return fail(LDPC_ERR_ARG, "NULL argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    unsigned long long h[8];
+    CUDA_TRY(cudaMemcpy(h, c->d_stats, sizeof(h), cudaMemcpyDeviceToHost));
+    out->frames = (int64_t)h[0]; out->ldpc_errors = (int64_t)h[1]; out->rs_errors = (int64_t)h[2];
+    out->ml_attempts = (int64_t)h[3]; out->ml_failures = (int64_t)h[4];
+    return LDPC_OK;
+}
+
+extern "C" int ldpc_reset_stats(ldpc_ctx *c)
+{
+    if (!c) return fail(LDPC_ERR_ARG, "NULL context");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemset(c->d_stats, 0, 8 * sizeof(unsigned long long)));
+    return LDPC_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// host-buffer entry points: chunked, double-buffered over two streams so that the copy of
+// chunk i+1 overlaps the kernels and the read-back of chunk i.
+// ------------------------------------------------------------------------------------------
+static int ensure_host_pipeline(ldpc_ctx *c)
+{
+    if (c->hstream[0]) return LDPC_OK;
+    const size_t per_cw = size_t(c->code.n) * c->S;
+    long long chunk = std::min<long long>(c->max_batch, std::max<long long>(256, (256ll << 20) / (long long)per_cw));
+    c->host_chunk = chunk;
+    for (int i = 0; i < 2; i++) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&c->hstream[i], cudaStreamNonBlocking));
+        CUDA_TRY(cudaMalloc(&c->h_in[i], size_t(chunk) * per_cw));
+        CUDA_TRY(cudaMalloc(&c->h_out[i], size_t(chunk) * per_cw));
+        CUDA_TRY(cudaMalloc(&c->h_mask[i], size_t(chunk) * c->NW * 4));
+        CUDA_TRY(cudaMalloc(&c->h_fail[i], size_t(chunk)));
+    }
+    return LDPC_OK;
+}
+
+extern "C" int ldpc_encode_host(ldpc_ctx *c, const void *h_info, void *h_cw, int64_t B)
+{
+    if (!c || !h_info || !h_cw || B < 0) return fail(LDPC_ERR_ARG, "bad argument to ldpc_encode_host");
+    CUDA_TRY(cudaSetDevice(c->device));
+    int rc = ensure_host_pipeline(c);
+    if (rc) return rc;
+    const size_t in_cw = size_t(c->code.k) * c->S, out_cw = size_t(c->code.n) * c->S;
+    int i = 0;
+    for (long long b0 = 0; b0 < B; b0 += c->host_chunk, i ^= 1) {
+        const long long nb = std::min<long long>(c->host_chunk, B - b0);
+        cudaStream_t st = c->hstream[i];
+        CUDA_TRY(cudaMemcpyAsync(c->h_in[i], static_cast<const uint8_t *>(h_info) + size_t(b0) * in_cw, size_t(nb) * in_cw,
+                                 cudaMemcpyHostToDevice, st));
+        rc = ldpc_encode(c, c->h_in[i], c->h_out[i], nb, st);
+        if (rc) return rc;
+        CUDA_TRY(cudaMemcpyAsync(static_cast<uint8_t *>(h_cw) + size_t(b0) * out_cw, c->h_out[i], size_t(nb) * out_cw,
+                                 cudaMemcpyDeviceToHost, st));
+    }
+    CUDA_TRY(cudaStreamSynchronize(c->hstream[0]));
+    CUDA_TRY(cudaStreamSynchronize(c->hstream[1]));
+    return LDPC_OK;
+}
+
+extern "C" int ldpc_decode_host(ldpc_ctx *c, const void *h_cw, const uint32_t *h_mask, void *h_out, uint8_t *h_fail,
+                                int max_iter, int mode, int64_t B)
+{
+    if (!c || !h_cw || !h_mask || !h_out || B < 0) return fail(LDPC_ERR_ARG, "bad argument to ldpc_decode_host");
+    CUDA_TRY(cudaSetDevice(c->device));
+    int rc = ensure_host_pipeline(c);
+    if (rc) return rc;
+    const size_t in_cw = size_t(c->code.n) * c->S, out_cw = size_t(c->code.k) * c->S;
+    // the scratch (schedule blobs) is shared by both streams: the peel/exec pair of chunk i+1 is ordered
+    // after the pair of chunk i by an event, while the copies on either side overlap freely
+    cudaEvent_t ev;
+    CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    int i = 0;
+    bool have_ev = false;
+    for (long long b0 = 0; b0 < B; b0 += c->host_chunk, i ^= 1) {
+        const long long nb = std::min<long long>(c->host_chunk, B - b0);
+        cudaStream_t st = c->hstream[i];
+        CUDA_TRY(cudaMemcpyAsync(c->h_in[i], static_cast<const uint8_t *>(h_cw) + size_t(b0) * in_cw, size_t(nb) * in_cw,
+                                 cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(c->h_mask[i], h_mask + size_t(b0) * c->NW, size_t(nb) * c->NW * 4, cudaMemcpyHostToDevice, st));
+        if (have_ev) CUDA_TRY(cudaStreamWaitEvent(st, ev, 0));
+        rc = ldpc_decode(c, c->h_in[i], c->h_mask[i], c->h_out[i], c->h_fail[i], max_iter, mode, nb, st);
+        if (rc) { cudaEventDestroy(ev); return rc; }
+        CUDA_TRY(cudaEventRecord(ev, st));
+        have_ev = true;
+        CUDA_TRY(cudaMemcpyAsync(static_cast<uint8_t *>(h_out) + size_t(b0) * out_cw, c->h_out[i], size_t(nb) * out_cw,
+                                 cudaMemcpyDeviceToHost, st));
+        if (h_fail) CUDA_TRY(cudaMemcpyAsync(h_fail + b0, c->h_fail[i], size_t(nb), cudaMemcpyDeviceToHost, st));
+    }
+    CUDA_TRY(cudaStreamSynchronize(c->hstream[0]));
+    CUDA_TRY(cudaStreamSynchronize(c->hstream[1]));
+    cudaEventDestroy(ev);
+    return LDPC_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Reed-Solomon entry points live in rs_gf256.cuh (rs_* functions below forward to it)
+// ------------------------------------------------------------------------------------------
+extern "C" int rs_ctx_create(rs_ctx **out, int n, int k, int symbol_bytes, int device, int64_t max_batch)
+{
+    return rs_create_impl(out, n, k, symbol_bytes, device, max_batch, g_err);
+}
+extern "C" int rs_ctx_destroy(rs_ctx *ctx) { return rs_destroy_impl(ctx); }
+extern "C" int rs_ctx_get_generator(const rs_ctx *ctx, uint8_t *gsys) { return rs_get_generator_impl(ctx, gsys, g_err); }
+extern "C" int rs_encode(rs_ctx *ctx, const void *d_info, void *d_cw, int64_t B, void *stream)
+{
+    return rs_encode_impl(ctx, d_info, d_cw, B, static_cast<cudaStream_t>(stream), g_err);
+}
+extern "C" int rs_decode(rs_ctx *ctx, const void *d_cw, const uint32_t *d_mask, void *d_out, uint8_t *d_fail, int64_t B,
+                         void *stream)
+{
+    return rs_decode_impl(ctx, d_cw, d_mask, d_out, d_fail, B, static_cast<cudaStream_t>(stream), g_err);
+}
