@@ -152,6 +152,20 @@ int ldpc_decode(ldpc_ctx *ctx, const void *d_cw, const uint32_t *d_mask, void *d
 int ldpc_get_stats(ldpc_ctx *ctx, ldpc_stats *out);
 int ldpc_reset_stats(ldpc_ctx *ctx);
 
+/* ---- profiling ----------------------------------------------------------------------
+ * Replaces CL_QUEUE_PROFILING_ENABLE + getStartEndTime(kernel_event) (main.cpp:515,:652):
+ * when enabled, every kernel the context launches is bracketed by CUDA events on the
+ * launching stream; ldpc_profile_read() synchronises and returns per-kernel device time.
+ * Launch counters are always maintained.                                                 */
+enum { LDPC_K_PEEL = 0, LDPC_K_EXEC_DECODE = 1, LDPC_K_EXEC_ENCODE = 2, LDPC_K_HYBRID = 3,
+       LDPC_K_CHANNEL = 4, LDPC_K_KINDS = 8 };
+typedef struct ldpc_profile {
+    double ms[LDPC_K_KINDS];        /* summed device time per kernel kind (profiling on)  */
+    int64_t launches[LDPC_K_KINDS]; /* kernel launches per kind since create / last reset */
+} ldpc_profile;
+int ldpc_profile_enable(ldpc_ctx *ctx, int on);
+int ldpc_profile_read(ldpc_ctx *ctx, ldpc_profile *out, int reset);
+
 /* ---- host-buffer entry points -------------------------------------------------------
  * The reference's run() (main.cpp:555-659): blocking host->device copy, kernels, blocking
  * device->host copy.  Host pointers (pinned memory makes the copies asynchronous and

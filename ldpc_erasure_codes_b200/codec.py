@@ -140,6 +140,15 @@ class LdpcCodec:
     def reset_stats(self):
         _lib.check(self.lib.ldpc_reset_stats(self._h))
 
+    # ---- CL_QUEUE_PROFILING_ENABLE / getStartEndTime ---------------------------------------
+    def profile_enable(self, on=True):
+        _lib.check(self.lib.ldpc_profile_enable(self._h, 1 if on else 0))
+
+    def profile_read(self, reset=True):
+        p = _lib.Profile()
+        _lib.check(self.lib.ldpc_profile_read(self._h, C.byref(p), 1 if reset else 0))
+        return {name: dict(ms=p.ms[i], launches=p.launches[i]) for i, name in enumerate(_lib.KIND_NAMES)}
+
 
 def fill_random(t: torch.Tensor, seed: int, block0: int = 0):
     """Counter-based synthetic payload (Threefry key {2, seed}); t must be a CUDA byte tensor."""

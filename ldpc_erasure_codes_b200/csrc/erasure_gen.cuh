@@ -6,7 +6,7 @@
 // :75,:96), erased iff ((int)out.v[0] & 0x3F) < PER_numerator_div_64 (:105).
 // IID32 (extension) compares the whole 32-bit word against a threshold.
 // Bursty model = Matlab/Bursty_Error_Channel_Model_Generator.m:12-47 with u1 = v[0]/2^32,
-// u2 = v[1]/2^32 of the same counter (extension, shared with the oracle).  The chain state at
+// u2 = v[1]/2^32 of the same counter (extension; the CPU checker defines the draws the same way).  The chain state at
 // the start of a codeword is recovered exactly and independently of batch sharding by walking
 // BACKWARDS over the transition uniforms to the nearest symbol whose state map is constant
 // (both states lead to the same next state) or to the beginning of the stream (state 0).

@@ -42,6 +42,19 @@ static int fail(int code, const std::string &msg)
             return fail(LDPC_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));  \
     } while (0)
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per-function process state: raise it once to the
+// device maximum (minus the kernel's static shared memory) instead of per-context values
+static int allow_max_smem(const void *func, int smem_optin)
+{
+    static std::vector<const void *> done;
+    for (const void *f : done) if (f == func) return LDPC_OK;
+    cudaFuncAttributes a;
+    CUDA_TRY(cudaFuncGetAttributes(&a, func));
+    CUDA_TRY(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin - int(a.sharedSizeBytes)));
+    done.push_back(func);
+    return LDPC_OK;
+}
+
 // LDPC_CUDA_DEBUG_SYNC=1: synchronise after every launch so that a faulting kernel is named
 static int debug_sync(const char *what, cudaStream_t st)
 {
@@ -132,6 +145,25 @@ struct ldpc_ctx {
     uint32_t *h_mask[2] = {nullptr, nullptr};
     uint8_t *h_fail[2] = {nullptr, nullptr};
     long long host_chunk = 0;
+    // profiling
+    bool prof_on = false;
+    struct ProfRec { cudaEvent_t a, b; int kind; };
+    std::vector<ProfRec> prof_recs;
+    long long launches[LDPC_K_KINDS] = {0, 0, 0, 0, 0, 0, 0, 0};
+};
+
+// brackets one kernel launch with events when profiling is on; always counts the launch
+struct ProfScope {
+    ldpc_ctx *c; cudaStream_t st; int kind; cudaEvent_t a = nullptr, b = nullptr;
+    ProfScope(ldpc_ctx *c_, int kind_, cudaStream_t st_) : c(c_), st(st_), kind(kind_)
+    {
+        c->launches[kind]++;
+        if (c->prof_on && cudaEventCreate(&a) == cudaSuccess && cudaEventCreate(&b) == cudaSuccess) cudaEventRecord(a, st);
+    }
+    ~ProfScope()
+    {
+        if (a && b) { cudaEventRecord(b, st); c->prof_recs.push_back({a, b, kind}); }
+    }
 };
 
 static const struct { const char *name; int n, k, rs_n, rs_k; } kBuiltin[] = {
@@ -167,12 +199,12 @@ static int choose_geom(const ldpc_ctx *c, bool dynamic_sched, ExecGeom *g)
         int nslot;
         if (dynamic_sched) nslot = (c->smem_optin - fixed) / (slot + blob);
         else nslot = (c->smem_optin - fixed - blob) / slot;
-        nslot = std::min(nslot, 4);
+        nslot = std::min(nslot, kExecMaxGroups);
         if (c->force_slots) nslot = std::min(nslot, c->force_slots);
         if (nslot < 1) continue;
         ExecGeom cand;
         cand.W = W; cand.nslot = nslot; cand.slot_bytes = slot; cand.sched_area = blob;
-        cand.smem_bytes = nslot * slot + (dynamic_sched ? nslot : 1) * blob + cidx_bytes + 2 * 8 * 8;
+        cand.smem_bytes = nslot * slot + (dynamic_sched ? nslot : 1) * blob + cidx_bytes + 2 * 8 * 8 + 64;
         if (!best.W || (best.nslot < 3 && cand.nslot > best.nslot)) best = cand;
         if (best.nslot >= 3) break;
     }
@@ -188,6 +220,7 @@ static void free_ctx(ldpc_ctx *c)
     cudaFree(c->d_cidx); cudaFree(c->d_vadj); cudaFree(c->d_enc_blob); cudaFree(c->d_sched);
     cudaFree(c->d_sched_len); cudaFree(c->d_resid); cudaFree(c->d_stats); cudaFree(c->d_fail_scratch);
     hybrid_free(c->hyb);
+    for (auto &r : c->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (int i = 0; i < 2; i++) {
         if (c->hstream[i]) cudaStreamDestroy(c->hstream[i]);
         cudaFree(c->h_in[i]); cudaFree(c->h_out[i]); cudaFree(c->h_mask[i]); cudaFree(c->h_fail[i]);
@@ -195,20 +228,31 @@ static void free_ctx(ldpc_ctx *c)
     delete c;
 }
 
+typedef void (*PeelKernel)(const PeelParams);
+
+static PeelKernel pick_peel(int MW, int VW)
+{
+    const int bmw = peel_bitmap_words(MW);
+    if (VW == 4) return bmw == 16 ? peel_schedule_kernel<2, 4> : (bmw == 32 ? peel_schedule_kernel<4, 4> : peel_schedule_kernel<8, 4>);
+    if (VW == 8) return bmw == 16 ? peel_schedule_kernel<2, 8> : (bmw == 32 ? peel_schedule_kernel<4, 8> : peel_schedule_kernel<8, 8>);
+    return nullptr;
+}
+
 static int setup_peel(ldpc_ctx *c)
 {
+    if (c->MW > 64 || (c->code.VW != 4 && c->code.VW != 8))
+        return fail(LDPC_ERR_UNSUPPORTED, "peel kernel supports m <= 2048 and column weight <= 8");
     const int tables = c->code.n * c->code.VW * 2 + c->code.m * c->code.RW * 2;
     const int per_group = peel_group_words(c->code.m, c->MW, c->NW) * 4;
-    const int G = 8;
-    int groups = (c->smem_optin - 64 - tables) / per_group;
+    const int G = kPeelG;
+    int groups = (c->smem_optin - 2048 - tables) / per_group;   // 2 KB margin: static + reserved shared memory
     groups = std::min(groups, 1024 / G);
     groups = (groups / (32 / G)) * (32 / G);
     if (groups < 32 / G) return fail(LDPC_ERR_UNSUPPORTED, "code too large for the peel kernel's shared memory");
     c->peel_G = G;
     c->peel_groups = groups;
     c->peel_smem = tables + groups * per_group;
-    CUDA_TRY(cudaFuncSetAttribute(peel_schedule_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->peel_smem));
-    return LDPC_OK;
+    return allow_max_smem(reinterpret_cast<const void *>(pick_peel(c->MW, c->code.VW)), c->smem_optin);
 }
 
 extern "C" int ldpc_ctx_create(ldpc_ctx **out, const char *h_mat_path, int code_ind, int symbol_bytes, int device,
@@ -341,23 +385,28 @@ extern "C" int ldpc_ctx_set_exec_geometry(ldpc_ctx *c, int slice_bytes, int slot
 // ------------------------------------------------------------------------------------------
 typedef void (*ExecKernel)(const CUtensorMap, const CUtensorMap, const ExecParams);
 
-static ExecKernel pick_exec(int W, int RWQ)
+// instantiated member counts: 7 / 14 are the committed codes' maximum row weights
+static ExecKernel pick_exec(int W, int max_row_weight, int *rwm_out)
 {
-    switch (W * 8 + RWQ) {
-        case 16 * 8 + 1: return payload_exec_kernel<16, 1>;
-        case 16 * 8 + 2: return payload_exec_kernel<16, 2>;
-        case 16 * 8 + 3: return payload_exec_kernel<16, 3>;
-        case 16 * 8 + 4: return payload_exec_kernel<16, 4>;
-        case 32 * 8 + 1: return payload_exec_kernel<32, 1>;
-        case 32 * 8 + 2: return payload_exec_kernel<32, 2>;
-        case 32 * 8 + 3: return payload_exec_kernel<32, 3>;
-        case 32 * 8 + 4: return payload_exec_kernel<32, 4>;
-        case 64 * 8 + 1: return payload_exec_kernel<64, 1>;
-        case 64 * 8 + 2: return payload_exec_kernel<64, 2>;
-        case 64 * 8 + 3: return payload_exec_kernel<64, 3>;
-        case 64 * 8 + 4: return payload_exec_kernel<64, 4>;
-        default: return nullptr;
+    static const int kRwm[] = {7, 8, 14, 16, 24, 32};
+    int rwm = 0;
+    for (int r : kRwm) if (r >= max_row_weight) { rwm = r; break; }
+    *rwm_out = rwm;
+#define PICK(WW)                                                      \
+    switch (rwm) {                                                    \
+        case 7: return payload_exec_kernel<WW, 7>;                    \
+        case 8: return payload_exec_kernel<WW, 8>;                    \
+        case 14: return payload_exec_kernel<WW, 14>;                  \
+        case 16: return payload_exec_kernel<WW, 16>;                  \
+        case 24: return payload_exec_kernel<WW, 24>;                  \
+        case 32: return payload_exec_kernel<WW, 32>;                  \
+        default: return nullptr;                                      \
     }
+    if (W == 16) { PICK(16) }
+    if (W == 32) { PICK(32) }
+    if (W == 64) { PICK(64) }
+#undef PICK
+    return nullptr;
 }
 
 static int launch_exec(ldpc_ctx *c, const ExecGeom &g, const void *d_in, int rows_in, void *d_out, int rows_out,
@@ -375,11 +424,16 @@ static int launch_exec(ldpc_ctx *c, const ExecGeom &g, const void *d_in, int row
     p.sched_max = g.sched_area; p.m = c->code.m; p.RW = c->code.RW; p.rows_in = rows_in; p.rows_out = rows_out;
     p.nbox_in = (rows_in + kBoxRows - 1) / kBoxRows; p.nbox_out = (rows_out + kBoxRows - 1) / kBoxRows;
     p.slices = c->S / g.W; p.nslot = g.nslot; p.slot_bytes = g.slot_bytes;
-    ExecKernel k = pick_exec(g.W, c->code.RW / 8);
-    if (!k) return fail(LDPC_ERR_UNSUPPORTED, "no executor instantiation for this slice width / row weight");
-    CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem_bytes));
+    int rwm = 0;
+    ExecKernel k = pick_exec(g.W, c->code.max_row_weight, &rwm);
+    if (!k || (rwm + 7) / 8 * 8 != c->code.RW) return fail(LDPC_ERR_UNSUPPORTED, "no executor instantiation for this slice width / row weight");
+    rc = allow_max_smem(reinterpret_cast<const void *>(k), c->smem_optin);
+    if (rc) return rc;
     const int grid = int(std::min<long long>(c->num_sms, B));
-    k<<<grid, kExecThreads, g.smem_bytes, st>>>(in_map, out_map, p);
+    {
+        ProfScope ps(c, sched_stride ? LDPC_K_EXEC_DECODE : LDPC_K_EXEC_ENCODE, st);
+        k<<<grid, g.nslot * kExecWarpsPerGroup * 32, g.smem_bytes, st>>>(in_map, out_map, p);
+    }
     CUDA_TRY(cudaGetLastError());
     return debug_sync(sched_stride ? "payload_exec_kernel(decode)" : "payload_exec_kernel(encode)", st);
 }
@@ -389,7 +443,9 @@ static int launch_exec(ldpc_ctx *c, const ExecGeom &g, const void *d_in, int row
 // ------------------------------------------------------------------------------------------
 extern "C" int ldpc_encode(ldpc_ctx *c, const void *d_info, void *d_cw, int64_t B, void *stream)
 {
-    if (!c || !d_info || !d_cw || B < 0) return fail(LDPC_ERR_ARG, "bad argument to ldpc_encode");
+    if (!c || B < 0) return fail(LDPC_ERR_ARG, "bad argument to ldpc_encode");
+    if (B == 0) return LDPC_OK;
+    if (!d_info || !d_cw) return fail(LDPC_ERR_ARG, "NULL buffer passed to ldpc_encode");
     if (!c->code.triangular)
         return fail(LDPC_ERR_NOT_TRIANGULAR, "H is not in triangular form (last entry of row r must be column k + r)");
     CUDA_TRY(cudaSetDevice(c->device));
@@ -437,6 +493,7 @@ extern "C" int ldpc_gen_erasures(ldpc_ctx *c, const ldpc_erasure_model *model, u
         }
         const long long warps = B * c->NW;
         const int grid = int(std::min<long long>((warps + 7) / 8, (long long)c->num_sms * 32));
+        ProfScope ps(c, LDPC_K_CHANNEL, st);
         gen_erasures_iid_kernel<<<grid, threads, 0, st>>>(p);
     } else if (model->model == LDPC_ERASURE_BURSTY) {
         if (!(model->bias > 0.0)) return fail(LDPC_ERR_ARG, "bursty model needs bias > 0");
@@ -448,6 +505,7 @@ extern "C" int ldpc_gen_erasures(ldpc_ctx *c, const ldpc_erasure_model *model, u
         if (p.t_p01 == p.t_p10 && p.a_p01 == p.a_p10)
             return fail(LDPC_ERR_UNSUPPORTED, "bursty model with bias == 1 has no resynchronising symbols");
         const int grid = int(std::min<long long>((B + 7) / 8, (long long)c->num_sms * 32));
+        ProfScope ps(c, LDPC_K_CHANNEL, st);
         gen_erasures_bursty_kernel<<<grid, threads, 0, st>>>(p);
     } else {
         return fail(LDPC_ERR_ARG, "unknown erasure model");
@@ -456,6 +514,7 @@ extern "C" int ldpc_gen_erasures(ldpc_ctx *c, const ldpc_erasure_model *model, u
     if (d_payload) {
         const long long warps = B * c->NW;
         const int grid = int(std::min<long long>((warps + 7) / 8, (long long)c->num_sms * 32));
+        ProfScope ps(c, LDPC_K_CHANNEL, st);
         zero_erased_kernel<<<grid, threads, 0, st>>>(d_mask, static_cast<uint8_t *>(d_payload), B, c->code.n, c->NW, c->S);
         CUDA_TRY(cudaGetLastError());
     }
@@ -488,7 +547,10 @@ static int decode_chunk(ldpc_ctx *c, const uint8_t *d_cw, const uint32_t *d_mask
     pp.max_iter = max_iter; pp.rs_n = c->rs_n; pp.rs_k = c->rs_k; pp.groups_per_block = c->peel_groups;
     pp.count_stats = 1;
     const int grid = int(std::min<long long>(c->num_sms, (B + c->peel_groups - 1) / c->peel_groups));
-    peel_schedule_kernel<8><<<grid, c->peel_groups * c->peel_G, c->peel_smem, st>>>(pp);
+    {
+        ProfScope ps(c, LDPC_K_PEEL, st);
+        pick_peel(c->MW, c->code.VW)<<<grid, c->peel_groups * c->peel_G, c->peel_smem, st>>>(pp);
+    }
     CUDA_TRY(cudaGetLastError());
     { int rcd = debug_sync("peel_schedule_kernel", st); if (rcd) return rcd; }
     int rc = launch_exec(c, c->dec, d_cw, c->code.n, d_out, c->code.k, c->d_sched, c->d_sched_len, c->sched_stride, B, st);
@@ -504,7 +566,9 @@ static int decode_chunk(ldpc_ctx *c, const uint8_t *d_cw, const uint32_t *d_mask
 extern "C" int ldpc_decode(ldpc_ctx *c, const void *d_cw, const uint32_t *d_mask, void *d_out, uint8_t *d_fail,
                            int max_iter, int mode, int64_t B, void *stream)
 {
-    if (!c || !d_cw || !d_mask || !d_out || B < 0) return fail(LDPC_ERR_ARG, "bad argument to ldpc_decode");
+    if (!c || B < 0) return fail(LDPC_ERR_ARG, "bad argument to ldpc_decode");
+    if (B == 0) return LDPC_OK;
+    if (!d_cw || !d_mask || !d_out) return fail(LDPC_ERR_ARG, "NULL buffer passed to ldpc_decode");
     if (mode != LDPC_MODE_PEEL && mode != LDPC_MODE_HYBRID) return fail(LDPC_ERR_ARG, "unknown decode mode");
     if (max_iter < 0 || max_iter > 1000000) return fail(LDPC_ERR_ARG, "max_iter out of range");
     CUDA_TRY(cudaSetDevice(c->device));
@@ -540,6 +604,35 @@ extern "C" int ldpc_reset_stats(ldpc_ctx *c)
     CUDA_TRY(cudaSetDevice(c->device));
     CUDA_TRY(cudaDeviceSynchronize());
     CUDA_TRY(cudaMemset(c->d_stats, 0, 8 * sizeof(unsigned long long)));
+    return LDPC_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// profiling
+// ------------------------------------------------------------------------------------------
+extern "C" int ldpc_profile_enable(ldpc_ctx *c, int on)
+{
+    if (!c) return fail(LDPC_ERR_ARG, "NULL context");
+    c->prof_on = on != 0;
+    return LDPC_OK;
+}
+
+extern "C" int ldpc_profile_read(ldpc_ctx *c, ldpc_profile *out, int reset)
+{
+    if (!c || !out) return fail(LDPC_ERR_ARG, "NULL argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    memset(out, 0, sizeof(*out));
+    for (auto &r : c->prof_recs) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) out->ms[r.kind] += ms;
+    }
+    for (int i = 0; i < LDPC_K_KINDS; i++) out->launches[i] = c->launches[i];
+    if (reset) {
+        for (auto &r : c->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+        c->prof_recs.clear();
+        for (int i = 0; i < LDPC_K_KINDS; i++) c->launches[i] = 0;
+    }
     return LDPC_OK;
 }
 

@@ -4,9 +4,9 @@
 // order, num_iter times, and a check fires when exactly one of its members is erased.  Which
 // check recovers which symbol, and in which sweep, depends only on the erasure pattern -- not
 // on the payload.  This kernel replays that serial schedule EXACTLY on the erasure mask alone
-// (one group of G lanes per codeword) and emits, per codeword, the list of (check, symbol)
-// recoveries grouped into dependency levels.  The payload executor (payload_exec.cuh) then
-// applies the list to the symbol payload with wide XORs, level by level.
+// and emits, per codeword, the list of (check, symbol) recoveries grouped into dependency
+// levels.  The payload executor (payload_exec.cuh) then applies the list to the symbol payload
+// with wide XORs, level by level.
 //
 // Exactness: a check is "pending" once its erased-member count is 1.  Pending checks are kept
 // in two bitmaps -- `cur` (still to be visited in this sweep: index above the check being
@@ -15,16 +15,21 @@
 // reference's order; the sweep counter reproduces num_iter.  The early stop of
 // ldpc_erasure_decoder_old.pro:116-123 is output-neutral and implicit (nothing pending).
 //
+// Mapping: G = 8 lanes per codeword, four codewords per warp, and the four groups of a warp
+// run in LOCKSTEP (one loop, warp-uniform trip count, full-mask ballots/shuffles): diverged
+// sub-warp groups would be serialised by the SIMT scheduler.  Per-codeword shared state is
+// 2.4 KB for (2040,1530), so ~72 codewords are in flight per SM.  All shared accesses go
+// through one base pointer and 32-bit word offsets (the cur/nxt swap is an offset swap).
+//
 // Per-check state word: [cnt:5 | level:11 | xor of erased member indices:16].  With cnt == 1
-// the xor field IS the erased member.  `level` = deepest recovery this check has seen among
-// its members; the recovery it performs itself gets level + 1.
+// the xor field IS the erased member.  `level` = deepest recovery seen among the check's
+// members; the recovery the check performs itself gets level + 1.  A check that has fired is
+// marked cnt = 31 with (level, symbol) of its recovery kept in the word, so the recovery list
+// is read back from the state array (no separate entry list).
 #pragma once
-#include <cooperative_groups.h>
-
 #include "device_utils.cuh"
 
 namespace ldpc {
-namespace cg = cooperative_groups;
 
 struct PeelParams {
     const uint32_t *mask;       // [B][NW]
@@ -39,7 +44,15 @@ struct PeelParams {
     int n, k, m, RW, VW, NW, MW, stride, max_iter, rs_n, rs_k, groups_per_block, count_stats;
 };
 
-__host__ __device__ inline int peel_group_words(int m, int MW, int NW) { return 3 * m + 2 + 2 * MW + NW; }
+constexpr int kPeelG = 8;
+constexpr uint32_t kFired = 31u;
+
+// per-codeword shared words: state[m] | cur[BMW] | nxt[BMW] | msk[NW + 1] + 3 scratch words, each 4-word aligned
+__host__ __device__ inline int peel_bitmap_words(int MW) { return MW <= 16 ? 16 : (MW <= 32 ? 32 : 64); }
+__host__ __device__ inline int peel_group_words(int m, int MW, int NW)
+{
+    return ((m + 3) & ~3) + 2 * peel_bitmap_words(MW) + ((NW + 4 + 3) & ~3);
+}
 
 __device__ __forceinline__ int popc_range(const uint32_t *w, int lo, int hi)  // bits [lo, hi)
 {
@@ -54,172 +67,228 @@ __device__ __forceinline__ int popc_range(const uint32_t *w, int lo, int hi)  //
     return cnt;
 }
 
-template <int G>
+__device__ __forceinline__ int group_sum(int v)  // over the 8 lanes of a group (xor < 8 stays inside it)
+{
+    v += __shfl_xor_sync(0xFFFFFFFFu, v, 4);
+    v += __shfl_xor_sync(0xFFFFFFFFu, v, 2);
+    v += __shfl_xor_sync(0xFFFFFFFFu, v, 1);
+    return v;
+}
+__device__ __forceinline__ uint32_t group_max(uint32_t v)
+{
+    v = max(v, __shfl_xor_sync(0xFFFFFFFFu, v, 4));
+    v = max(v, __shfl_xor_sync(0xFFFFFFFFu, v, 2));
+    v = max(v, __shfl_xor_sync(0xFFFFFFFFu, v, 1));
+    return v;
+}
+
+template <int WPL, int VW>   // WPL = bitmap words per lane (2, 4, 8); VW = padded variable degree (4, 8)
 __global__ void __launch_bounds__(1024) peel_schedule_kernel(const PeelParams p)
 {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
+    constexpr int G = kPeelG;
+    constexpr int BMW = G * WPL;              // bitmap words per codeword
+    constexpr unsigned FULL = 0xFFFFFFFFu;
+    extern __shared__ __align__(16) uint32_t sh[];
     __shared__ unsigned int s_stat[4];
-    uint16_t *vadj_s = reinterpret_cast<uint16_t *>(smem_raw);
-    uint16_t *cidx_s = vadj_s + size_t(p.n) * p.VW;
-    uint32_t *grp_base = reinterpret_cast<uint32_t *>(cidx_s + size_t(p.m) * p.RW);
+    const int m = p.m, NW = p.NW, RW = p.RW;
+    const int m4 = (m + 3) & ~3;
+    const int vadj_words = (p.n * VW) / 2;    // u16 table sizes in 32-bit words
+    const int cidx_words = (m * RW) / 2;
+    uint16_t *vadj_s = reinterpret_cast<uint16_t *>(sh);
+    uint16_t *cidx_s = reinterpret_cast<uint16_t *>(sh + vadj_words);
+    const int grp_base = vadj_words + cidx_words;
+    const uint32_t padidx = uint32_t(NW) * 32u;   // row padding points at the always-zero word msk[NW]
 
-    {   // stage the adjacency tables (uint4 copies; both tables are multiples of 16 bytes)
+    {   // stage the adjacency tables; check-row padding is redirected to the zero mask bit
         const uint4 *src = reinterpret_cast<const uint4 *>(p.vadj);
-        uint4 *dst = reinterpret_cast<uint4 *>(vadj_s);
-        const int nv = (p.n * p.VW * 2) / 16;
-        for (int i = threadIdx.x; i < nv; i += blockDim.x) dst[i] = src[i];
-        src = reinterpret_cast<const uint4 *>(p.cidx);
-        dst = reinterpret_cast<uint4 *>(cidx_s);
-        const int nc = (p.m * p.RW * 2) / 16;
-        for (int i = threadIdx.x; i < nc; i += blockDim.x) dst[i] = src[i];
+        uint4 *dst = reinterpret_cast<uint4 *>(sh);
+        for (int i = threadIdx.x; i < vadj_words / 4; i += blockDim.x) dst[i] = src[i];
+        const uint32_t *s32 = reinterpret_cast<const uint32_t *>(p.cidx);
+        for (int i = threadIdx.x; i < cidx_words; i += blockDim.x) {
+            uint32_t w = s32[i];
+            if ((w & 0xFFFFu) == 0xFFFFu) w = (w & 0xFFFF0000u) | padidx;
+            if ((w >> 16) == 0xFFFFu) w = (w & 0xFFFFu) | (padidx << 16);
+            sh[vadj_words + i] = w;
+        }
         if (threadIdx.x < 4) s_stat[threadIdx.x] = 0;
     }
     __syncthreads();
 
-    auto tile = cg::tiled_partition<G>(cg::this_thread_block());
-    const int lane = tile.thread_rank();
+    const int wl = threadIdx.x & 31;          // lane in warp
+    const int lane = wl % G;                  // lane in group
+    const int gshift = wl - lane;             // first warp lane of this group
     const int grp = threadIdx.x / G;
-    const int m = p.m, MW = p.MW, NW = p.NW, RW = p.RW, VW = p.VW;
-
-    uint32_t *state = grp_base + size_t(grp) * peel_group_words(m, MW, NW);
-    uint32_t *ent = state + m;
-    uint32_t *lvlcnt = ent + m;          // m + 2 words
-    uint32_t *bm_a = lvlcnt + m + 2;
-    uint32_t *bm_b = bm_a + MW;
-    uint32_t *msk = bm_b + MW;
+    const int state_off = grp_base + grp * peel_group_words(m, p.MW, NW);
+    const int bma_off = state_off + m4;
+    const int bmb_off = bma_off + BMW;
+    const int msk_off = bmb_off + BMW;
+    const int LC = 2 * BMW + NW;              // level counters that fit in the dead bitmap/mask area
+    const int lc_off = bma_off;
+    const int dummy_off = msk_off + NW + 1 + lane % 3;   // scratch words behind the mask 
 
     unsigned int my_fail = 0, my_rs = 0, my_frames = 0;
+    const long long stride = (long long)gridDim.x * p.groups_per_block;
 
-    for (long long cw = (long long)blockIdx.x * p.groups_per_block + grp; cw < p.B;
-         cw += (long long)gridDim.x * p.groups_per_block) {
+    for (long long cw = (long long)blockIdx.x * p.groups_per_block + grp; __any_sync(FULL, cw < p.B); cw += stride) {
+        const bool valid = cw < p.B;
         // ---- 1. erasure mask -> shared, erasure counts ---------------------------------
-        const uint32_t *gm = p.mask + cw * NW;
-        int n_er = 0;
-        for (int w = lane; w < NW; w += G) {
-            uint32_t x = gm[w];
-            if (w == NW - 1 && (p.n & 31)) x &= 0xFFFFFFFFu >> (32 - (p.n & 31));
-            msk[w] = x;
+        int n_er = 0, rem_sys = 0;
+        for (int w = lane; w <= NW; w += G) {
+            uint32_t x = (valid && w < NW) ? p.mask[cw * NW + w] : 0u;
+            if (w == NW - 1 && (p.n & 31)) x &= FULL >> (32 - (p.n & 31));
+            sh[msk_off + w] = x;
             n_er += __popc(x);
+            const int b0 = w << 5;   // systematic part: bits below k
+            uint32_t xs = x;
+            if (b0 >= p.k) xs = 0u;
+            else if (b0 + 32 > p.k) xs &= FULL >> (b0 + 32 - p.k);
+            rem_sys += __popc(xs);
         }
-        for (int w = lane; w < MW; w += G) { bm_a[w] = 0; bm_b[w] = 0; }
-        tile.sync();
 #pragma unroll
-        for (int o = G / 2; o > 0; o >>= 1) n_er += tile.shfl_xor(n_er, o);
-        int rem_sys = 0;
-        if (lane == 0) rem_sys = popc_range(msk, 0, p.k);
-        rem_sys = tile.shfl(rem_sys, 0);
-        if (p.count_stats && p.rs_n > 0) {  // RS-equivalent MDS counting, perf_tests.cl:70-80
+        for (int i = 0; i < 2 * WPL; i++) sh[bma_off + lane + i * G] = 0u;
+        n_er = group_sum(n_er);
+        rem_sys = group_sum(rem_sys);
+        __syncwarp();
+        if (p.count_stats && p.rs_n > 0 && valid) {  // RS-equivalent MDS counting, perf_tests.cl:70-80
             for (int b = lane; b < p.n / p.rs_n; b += G)
-                if (popc_range(msk, b * p.rs_n, (b + 1) * p.rs_n) > p.rs_n - p.rs_k) my_rs++;
+                if (popc_range(sh + msk_off, b * p.rs_n, (b + 1) * p.rs_n) > p.rs_n - p.rs_k) my_rs++;
         }
 
         // ---- 2. per-check state from the mask ------------------------------------------
         for (int c = lane; c < m; c += G) {
-            const uint4 *row = reinterpret_cast<const uint4 *>(cidx_s + size_t(c) * RW);
+            const uint4 *row = reinterpret_cast<const uint4 *>(cidx_s + c * RW);
             uint32_t cnt = 0, x = 0;
             for (int q = 0; q < RW / 8; q++) {
                 const uint4 r4 = row[q];
                 const uint32_t rr[4] = {r4.x, r4.y, r4.z, r4.w};
 #pragma unroll
                 for (int t = 0; t < 8; t++) {
-                    const uint32_t u = (rr[t >> 1] >> ((t & 1) * 16)) & 0xFFFFu;
-                    if (u != 0xFFFFu) {
-                        const uint32_t bit = (msk[u >> 5] >> (u & 31)) & 1u;
-                        cnt += bit;
-                        x ^= bit ? u : 0u;
-                    }
+                    const uint32_t u = (t & 1) ? (rr[t >> 1] >> 16) : (rr[t >> 1] & 0xFFFFu);
+                    const uint32_t bit = (sh[msk_off + (u >> 5)] >> (u & 31)) & 1u;
+                    cnt += bit;
+                    x ^= (0u - bit) & u;
                 }
             }
-            state[c] = (cnt << 27) | x;
-            if (cnt == 1) atomicOr(&bm_a[c >> 5], 1u << (c & 31));
+            sh[state_off + c] = (cnt << 27) | x;
+            if (cnt == 1) atomicOr(&sh[bma_off + (c >> 5)], 1u << (c & 31));
         }
-        tile.sync();
+        __syncwarp();
 
-        // ---- 3. replay of the serial sweeps --------------------------------------------
-        uint32_t *cur = bm_a, *nxt = bm_b;
-        int sweep = 1, w0 = 0;
+        // ---- 3. replay of the serial sweeps, four codewords per warp in lockstep -------
+        int cur_off = bma_off, nxt_off = bmb_off;
+        int sweep = 1;
         uint32_t ne = 0;
-        while (n_er > 0 && p.max_iter > 0) {
-            int c = -1;
-            while (w0 < MW) {
-                const int w = w0 + lane;
-                const uint32_t x = (w < MW) ? cur[w] : 0u;
-                const unsigned b = tile.ballot(x != 0u);
-                if (b) {
-                    const int src = __ffs(b) - 1;
-                    const uint32_t xw = tile.shfl(x, src);
-                    c = ((w0 + src) << 5) + (__ffs(xw) - 1);
-                    if (lane == src) cur[w] = x & (x - 1u);
-                    w0 += src;
-                    break;
+        bool active = valid && n_er > 0 && p.max_iter > 0;
+        bool prev_empty = false;
+        while (__any_sync(FULL, active)) {
+            // lowest pending check of this sweep: lane L owns bitmap words [L*WPL, (L+1)*WPL)
+            uint32_t xs[WPL];
+            if (WPL == 2) {
+                const uint2 t = *reinterpret_cast<const uint2 *>(&sh[cur_off + lane * 2]);
+                xs[0] = t.x; xs[1] = t.y;
+            } else {
+#pragma unroll
+                for (int q = 0; q < WPL / 4; q++) {
+                    const uint4 t = *reinterpret_cast<const uint4 *>(&sh[cur_off + lane * WPL + q * 4]);
+                    xs[q * 4 + 0] = t.x; xs[q * 4 + 1] = t.y; xs[q * 4 + 2] = t.z; xs[q * 4 + 3] = t.w;
                 }
-                w0 += G;
             }
-            tile.sync();
-            if (c < 0) {  // sweep over: anything queued for the next one?
-                sweep++;
-                if (sweep > p.max_iter) break;
-                uint32_t *t = cur; cur = nxt; nxt = t;
-                w0 = 0;
-                bool any = false;
-                for (int w = lane; w < MW; w += G) any |= (cur[w] != 0u);
-                if (!tile.any(any)) break;
-                continue;
-            }
-            const uint32_t st = state[c];
-            if ((st >> 27) != 1u) continue;  // its symbol was recovered by an earlier check
-            const uint32_t v = st & 0xFFFFu;
+            int myc = -1;
+#pragma unroll
+            for (int i = WPL - 1; i >= 0; i--)
+                if (xs[i]) myc = ((lane * WPL + i) << 5) + __ffs(xs[i]) - 1;
+            const unsigned gb = (__ballot_sync(FULL, myc >= 0) >> gshift) & 0xFFu;
+            const int src = __ffs(gb) - 1;                                   // -1: nothing pending
+            const int c = __shfl_sync(FULL, myc, gshift + (src & 7));        // (src = -1 reads a lane whose myc is -1)
+            // Straight-line, select-based body: the four codewords of the warp take the same
+            // instruction path whatever they do this step (pop / stale pop / end of sweep / idle).
+            const bool pop = active && c >= 0;
+            const bool swp = active && c < 0;
+            if (pop && lane == src) atomicAnd(&sh[cur_off + (c >> 5)], ~(1u << (c & 31)));
+            const uint32_t st = sh[state_off + (pop ? c : 0)];
+            const bool fire = pop && (st >> 27) == 1u;   // else: its symbol was recovered by an earlier check
+            const uint32_t v = fire ? (st & 0xFFFFu) : 0u;
             const uint32_t lvl = ((st >> 16) & 0x7FFu) + 1u;
-            if (lane == 0) ent[ne] = v | (uint32_t(c) << 16);
-            ne++;
-            n_er--;
-            if (int(v) < p.k) rem_sys--;
-            for (int j = lane; j < VW; j += G) {
-                const uint32_t c2 = vadj_s[size_t(v) * VW + j];
-                if (c2 != 0xFFFFu) {
-                    const uint32_t s2 = state[c2];
-                    const uint32_t cnt2 = (s2 >> 27) - 1u;
-                    const uint32_t l2 = max((s2 >> 16) & 0x7FFu, lvl);
-                    state[c2] = (cnt2 << 27) | (l2 << 16) | ((s2 & 0xFFFFu) ^ v);
-                    if (cnt2 == 1u) {
-                        if (int(c2) > c) atomicOr(&cur[c2 >> 5], 1u << (c2 & 31));
-                        else atomicOr(&nxt[c2 >> 5], 1u << (c2 & 31));
-                    }
-                }
-            }
-            tile.sync();
+            ne += fire ? 1u : 0u;
+            n_er -= fire ? 1 : 0;
+            rem_sys -= (fire && int(v) < p.k) ? 1 : 0;
+            const uint32_t c2 = (lane < VW) ? vadj_s[v * VW + lane] : 0xFFFFu;
+            const bool upd = fire && c2 != 0xFFFFu;
+            const int a2 = upd ? state_off + int(c2) : dummy_off;        // idle lanes hit a scratch word
+            const uint32_t s2 = sh[a2];
+            const uint32_t cnt2 = (s2 >> 27) - 1u;
+            const uint32_t l2 = max((s2 >> 16) & 0x7FFu, lvl);
+            const bool self = int(c2) == c;
+            sh[a2] = self ? ((kFired << 27) | (lvl << 16) | v) : ((cnt2 << 27) | (l2 << 16) | ((s2 & 0xFFFFu) ^ v));
+            if (upd && !self && cnt2 == 1u)
+                atomicOr(&sh[(int(c2) > c ? cur_off : nxt_off) + (c2 >> 5)], 1u << (c2 & 31));
+            // end of sweep: swap the bitmaps; stop at the cap or at the fixed point (two empty sweeps)
+            sweep += swp ? 1 : 0;
+            const int t_off = cur_off;
+            cur_off = swp ? nxt_off : cur_off;
+            nxt_off = swp ? t_off : nxt_off;
+            active = active && n_er > 0 && !(swp && (sweep > p.max_iter || prev_empty));
+            prev_empty = swp ? true : (pop ? false : prev_empty);
+            __syncwarp();
         }
 
         // ---- 4. counting sort of the recoveries by level, blob to global ---------------
-        for (int i = lane; i < m + 2; i += G) lvlcnt[i] = 0;
-        tile.sync();
+        for (int i = lane; i < LC; i += G) sh[lc_off + i] = 0u;
+        __syncwarp();
         uint32_t nl = 0;
-        for (uint32_t e = lane; e < ne; e += G) {
-            const uint32_t L = (state[ent[e] >> 16] >> 16) & 0x7FFu;
-            atomicAdd(&lvlcnt[L], 1u);
-            nl = max(nl, L);
+        for (int c = lane; c < m; c += G) {
+            const uint32_t st = sh[state_off + c];
+            if (valid && (st >> 27) == kFired) {
+                const uint32_t L = (st >> 16) & 0x7FFu;
+                if (int(L) < LC) atomicAdd(&sh[lc_off + L], 1u);
+                nl = max(nl, L);
+            }
         }
-#pragma unroll
-        for (int o = G / 2; o > 0; o >>= 1) nl = max(nl, tile.shfl_xor(nl, o));
-        tile.sync();
-        uint8_t *blob = p.sched + cw * (long long)p.stride;
+        nl = group_max(nl);
+        __syncwarp();
+        uint8_t *blob = p.sched + (valid ? cw : 0) * (long long)p.stride;
         uint32_t *g_ent = reinterpret_cast<uint32_t *>(blob) + 4;
         uint16_t *g_off = reinterpret_cast<uint16_t *>(g_ent + ne);
-        uint32_t run = 0;  // exclusive scan over levels 1..nl, G at a time
-        for (uint32_t base = 1; base <= nl; base += G) {
-            const uint32_t L = base + lane;
-            const uint32_t cnt = (L <= nl) ? lvlcnt[L] : 0u;
-            uint32_t inc = cnt;
+        const unsigned gm = 0xFFu << gshift;
+        if (int(nl) < LC) {
+            uint32_t run = 0;  // exclusive scan over levels 1..nl, G at a time
+            for (uint32_t base = 1; base <= nl; base += G) {
+                const uint32_t L = base + lane;
+                const uint32_t cnt = (L <= nl) ? sh[lc_off + L] : 0u;
+                uint32_t inc = cnt;
 #pragma unroll
-            for (int o = 1; o < G; o <<= 1) {
-                const uint32_t t = tile.shfl_up(inc, o);
-                if (lane >= o) inc += t;
+                for (int o = 1; o < G; o <<= 1) {
+                    const uint32_t t = __shfl_up_sync(gm, inc, o, G);
+                    if (lane >= o) inc += t;
+                }
+                const uint32_t excl = run + inc - cnt;
+                if (L <= nl) { sh[lc_off + L] = excl; if (valid) g_off[L - 1] = uint16_t(excl); }
+                run += __shfl_sync(gm, inc, G - 1, G);
             }
-            const uint32_t excl = run + inc - cnt;
-            if (L <= nl) { lvlcnt[L] = excl; g_off[L - 1] = uint16_t(excl); }
-            run += tile.shfl(inc, G - 1);
+            __syncwarp(gm);
+            for (int c = lane; c < m; c += G) {
+                const uint32_t st = sh[state_off + c];
+                if (valid && (st >> 27) == kFired) {
+                    const uint32_t L = (st >> 16) & 0x7FFu;
+                    g_ent[atomicAdd(&sh[lc_off + L], 1u)] = (st & 0xFFFFu) | (uint32_t(c) << 16);
+                }
+            }
+        } else if (valid) {
+            // more levels than counters (never seen on the committed codes): one pass per level
+            uint32_t run = 0;
+            for (uint32_t L = 1; L <= nl; L++) {
+                if (lane == 0) g_off[L - 1] = uint16_t(run);
+                for (int c0 = 0; c0 < m; c0 += G) {
+                    const int c = c0 + lane;
+                    const uint32_t st = (c < m) ? sh[state_off + c] : 0u;
+                    const bool hit = (st >> 27) == kFired && ((st >> 16) & 0x7FFu) == L;
+                    const unsigned hb = (__ballot_sync(gm, hit) >> gshift) & 0xFFu;
+                    if (hit) g_ent[run + __popc(hb & ((1u << lane) - 1u))] = (st & 0xFFFFu) | (uint32_t(c) << 16);
+                    run += __popc(hb);
+                }
+            }
         }
-        if (lane == 0) {
+        if (valid && lane == 0) {
             g_off[nl] = uint16_t(ne);
             uint32_t *hdr = reinterpret_cast<uint32_t *>(blob);
             hdr[0] = ne; hdr[1] = nl; hdr[2] = uint32_t(n_er); hdr[3] = uint32_t(rem_sys);
@@ -229,13 +298,7 @@ __global__ void __launch_bounds__(1024) peel_schedule_kernel(const PeelParams p)
             my_frames++;
             if (rem_sys > 0) my_fail++;
         }
-        tile.sync();
-        for (uint32_t e = lane; e < ne; e += G) {
-            const uint32_t w = ent[e];
-            const uint32_t L = (state[w >> 16] >> 16) & 0x7FFu;
-            g_ent[atomicAdd(&lvlcnt[L], 1u)] = w;
-        }
-        tile.sync();
+        __syncwarp();
     }
 
     if (p.count_stats) {

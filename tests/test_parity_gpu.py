@@ -1,0 +1,240 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle on the same
+seeded inputs.  Bit-exact everywhere (byte / integer arithmetic only)."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import oracle as orc  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def codecs():
+    from ldpc_erasure_codes_b200.codec import LdpcCodec
+    cache = {}
+
+    def get(ci, S, max_batch=512):
+        key = (ci, S, max_batch)
+        if key not in cache:
+            cache[key] = LdpcCodec(code=ci, symbol_bytes=S, device=0, max_batch=max_batch)
+        return cache[key]
+    yield get
+    for c in cache.values():
+        c.close()
+
+
+def _np(t):
+    return t.cpu().numpy()
+
+
+def _rand_info(B, k, S, seed):
+    from ldpc_erasure_codes_b200.codec import fill_random
+    t = torch.empty((B, k, S), dtype=torch.uint8, device="cuda")
+    fill_random(t, seed=seed)
+    return t
+
+
+# ------------------------------------------------------------------------------- loader
+@pytest.mark.parametrize("ci", [0, 1, 2])
+def test_h_loader_matches_scipy(codecs, ci):
+    codec = codecs(ci, 64)
+    code = orc.Code.builtin(ci)
+    rp, cidx = codec.csr()
+    assert np.array_equal(rp, code.row_ptr) and np.array_equal(cidx, code.col_idx)
+    assert (codec.n, codec.k, codec.m) == (code.n, code.k, code.m)
+    assert codec.info.encode_levels == {0: 60, 1: 27, 2: 77}[ci]   # SURVEY a-3
+
+
+# ------------------------------------------------------------------------------- channel
+@pytest.mark.parametrize("ci,P,frame0", [(0, 19, 0), (1, 13, 0), (1, 9, 1000003), (2, 19, 5), (1, 0, 0), (1, 64, 0)])
+def test_iid64_generator_bit_exact(codecs, ci, P, frame0):
+    from ldpc_erasure_codes_b200.codec import unpack_mask
+    codec = codecs(ci, 64)
+    B = 37
+    mask = codec.gen_erasures(B, 12345, P=P, frame0=frame0)
+    ref = orc.gen_erasures_iid(codec.n, 12345, B, P=P, frame0=frame0)
+    assert np.array_equal(unpack_mask(mask, codec.n), ref)
+    # padding bits above n are zero
+    m = _np(mask).view(np.uint32)
+    if codec.n % 32:
+        assert not (m[:, -1] >> (codec.n % 32)).any()
+
+
+def test_iid32_and_counter_wrap(codecs):
+    from ldpc_erasure_codes_b200.codec import unpack_mask
+    codec = codecs(1, 64)
+    thr = int(0.2 * 2 ** 32)
+    frame0 = (2 ** 32) // 2040 - 3          # counter wraps inside this batch
+    mask = codec.gen_erasures(8, 777, p=0.2, frame0=frame0)
+    ref = orc.gen_erasures_iid(2040, 777, 8, p32=thr, frame0=frame0)
+    assert np.array_equal(unpack_mask(mask, 2040), ref)
+
+
+@pytest.mark.parametrize("params", [(0.001, 0.1, 10.0), (0.02, 0.4, 10.0), (0.3, 0.9, 2.0)])
+def test_bursty_generator_bit_exact_and_shard_independent(codecs, params):
+    from ldpc_erasure_codes_b200.codec import unpack_mask
+    codec = codecs(2, 64)
+    B = 24
+    ref, _ = orc.gen_erasures_bursty(4000, 99, B, *params)
+    mask = codec.gen_erasures(B, 99, bursty=params)
+    assert np.array_equal(unpack_mask(mask, 4000), ref)
+    # a shard that starts in the middle of the stream reproduces the same frames
+    part = codec.gen_erasures(B - 10, 99, bursty=params, frame0=10)
+    assert np.array_equal(unpack_mask(part, 4000), ref[10:])
+
+
+# ------------------------------------------------------------------------------- encoder
+@pytest.mark.parametrize("ci,S,B", [(0, 64, 20), (1, 64, 300), (2, 64, 20), (1, 16, 33), (1, 128, 9), (0, 1024, 5)])
+def test_encode_bit_exact(codecs, ci, S, B):
+    codec = codecs(ci, S)
+    info = _rand_info(B, codec.k, S, seed=ci * 100 + S)
+    cw = codec.encode(info)
+    ref = orc.encode(orc.Code.builtin(ci), _np(info))
+    assert np.array_equal(_np(cw), ref)
+
+
+def test_encode_survey_crosscheck(codecs):
+    import zlib
+    codec = codecs(1, 16)
+    v = (np.arange(1, codec.k + 1, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15)).view(np.uint8).reshape(codec.k, 8)
+    info = np.tile(v, (1, 2))[None]
+    cw = _np(codec.encode(torch.from_numpy(info).cuda()))[0]
+    assert zlib.crc32(np.ascontiguousarray(cw[:, :8]).tobytes()) == 0x91491f2f   # SURVEY 8(c), (2040,1530)
+
+
+# ------------------------------------------------------------------------------- peel decode
+def _scenario(codec, ci, B, P, seed, S, valid=True):
+    code = orc.Code.builtin(ci)
+    if valid:
+        info = _rand_info(B, codec.k, S, seed=seed)
+        cw = codec.encode(info)
+    else:   # arbitrary bytes, not a codeword: only an exact replay of the serial schedule matches
+        cw = _rand_info(B, codec.n, S, seed=seed + 1)
+    rx = cw.clone()
+    mask = codec.gen_erasures(B, seed, P=P, payload=rx)
+    flags = orc.gen_erasures_iid(code.n, seed, B, P=P)
+    return code, cw, rx, mask, flags
+
+
+@pytest.mark.parametrize("ci,S,P", [(1, 64, 6), (1, 64, 10), (1, 64, 13), (1, 64, 16), (1, 64, 19),
+                                    (0, 64, 19), (0, 64, 24), (2, 64, 19), (1, 16, 13), (1, 32, 13), (1, 128, 12),
+                                    (0, 1024, 19)])
+def test_peel_decode_bit_exact(codecs, ci, S, P):
+    codec = codecs(ci, S)
+    B = 12 if S >= 1024 else 200
+    code, cw, rx, mask, flags = _scenario(codec, ci, B, P, 4242 + P, S)
+    out, fail = codec.decode(rx, mask, max_iter=50)
+    ref = orc.decode(code, _np(rx), flags, max_iter=50)
+    assert np.array_equal(_np(fail), ref["fail_sys"])
+    assert np.array_equal(_np(out), ref["out"])
+    good = ref["fail_sys"] == 0
+    assert np.array_equal(_np(out)[good], _np(cw)[good][:, :code.k])
+
+
+@pytest.mark.parametrize("max_iter", [0, 1, 2, 3, 7, 10])
+def test_peel_decode_iteration_cap_is_exact(codecs, max_iter):
+    """A binding num_iter gives the reference's partial result: the serial sweep order is replayed exactly."""
+    codec = codecs(1, 64)
+    code, cw, rx, mask, flags = _scenario(codec, 1, 150, 12, 99, 64)
+    out, fail = codec.decode(rx, mask, max_iter=max_iter)
+    ref = orc.decode(code, _np(rx), flags, max_iter=max_iter, early_stop=False)
+    assert np.array_equal(_np(fail), ref["fail_sys"]) and np.array_equal(_np(out), ref["out"])
+
+
+@pytest.mark.parametrize("ci,P", [(1, 12), (0, 22)])
+def test_peel_decode_exact_on_non_codeword_input(codecs, ci, P):
+    codec = codecs(ci, 64)
+    code, cw, rx, mask, flags = _scenario(codec, ci, 120, P, 31337, 64, valid=False)
+    out, fail = codec.decode(rx, mask, max_iter=50)
+    ref = orc.decode(code, _np(rx), flags, max_iter=50)
+    assert np.array_equal(_np(fail), ref["fail_sys"]) and np.array_equal(_np(out), ref["out"])
+
+
+def test_peel_edge_cases(codecs):
+    from ldpc_erasure_codes_b200.codec import pack_mask
+    codec = codecs(1, 64)
+    code = orc.Code.builtin(1)
+    info = _rand_info(4, codec.k, 64, seed=5)
+    cw = codec.encode(info)
+    flags = np.zeros((4, code.n), np.uint8)
+    flags[1, :] = 1                      # everything erased
+    flags[2, code.k:] = 1                # all parities erased
+    flags[3, :code.k:2] = 1              # every other systematic symbol
+    rx = _np(cw).copy()
+    rx[flags == 1] = 0
+    out, fail = codec.decode(torch.from_numpy(rx).cuda(), torch.from_numpy(pack_mask(flags)).cuda(), max_iter=50)
+    ref = orc.decode(code, rx, flags, max_iter=50)
+    assert np.array_equal(_np(fail), ref["fail_sys"]) and np.array_equal(_np(out), ref["out"])
+    assert list(_np(fail)) == [0, 1, 0, int(ref["fail_sys"][3])]
+    # empty batch is a no-op
+    e_out, e_fail = codec.decode(torch.empty((0, code.n, 64), dtype=torch.uint8, device="cuda"),
+                                 torch.empty((0, codec.mask_words), dtype=torch.int32, device="cuda"))
+    assert e_out.shape[0] == 0
+
+
+@pytest.mark.parametrize("B", [1, 147, 149, 700])
+def test_ragged_batches_and_chunking(codecs, B):
+    codec = codecs(1, 64, max_batch=256)     # 700 > max_batch: internal chunking
+    code, cw, rx, mask, flags = _scenario(codec, 1, B, 13, 1000 + B, 64)
+    out, fail = codec.decode(rx, mask)
+    ref = orc.decode(code, _np(rx), flags, max_iter=50)
+    assert np.array_equal(_np(fail), ref["fail_sys"]) and np.array_equal(_np(out), ref["out"])
+
+
+@pytest.mark.parametrize("W,slots", [(16, 0), (32, 0), (64, 0), (32, 1), (32, 2), (16, 2)])
+def test_executor_geometries_agree(codecs, W, slots):
+    from ldpc_erasure_codes_b200.codec import LdpcCodec
+    codec = LdpcCodec(code=1, symbol_bytes=64, device=0, max_batch=512)
+    codec.set_exec_geometry(W, slots)
+    assert codec.info.slice_bytes == W
+    code, cw, rx, mask, flags = _scenario(codec, 1, 300, 13, 77, 64)
+    out, fail = codec.decode(rx, mask)
+    ref = orc.decode(code, _np(rx), flags, max_iter=50)
+    assert np.array_equal(_np(out), ref["out"]) and np.array_equal(_np(fail), ref["fail_sys"])
+    cw2 = codec.encode(_rand_info(50, codec.k, 64, seed=3))
+    assert np.array_equal(_np(cw2), orc.encode(code, _np(_rand_info(50, codec.k, 64, seed=3))))
+    codec.close()
+
+
+def test_statistics_match_reference_counters(codecs):
+    codec = codecs(1, 64)
+    code, cw, rx, mask, flags = _scenario(codec, 1, 400, 13, 2024, 64)
+    codec.reset_stats()
+    out, fail = codec.decode(rx, mask)
+    st = codec.stats()
+    ref = orc.decode(code, _np(rx), flags, max_iter=50)
+    assert st["frames"] == 400 and st["ldpc_errors"] == int(ref["fail_sys"].sum())
+    assert st["rs_errors"] == sum(orc.rs_mds_count(code.n, 255, 192, f) for f in flags)   # perf_tests.cl:70-80
+
+
+def test_host_buffer_entry_points(codecs):
+    codec = codecs(1, 64, max_batch=256)
+    code, cw, rx, mask, flags = _scenario(codec, 1, 600, 12, 8, 64)
+    h_out, h_fail = codec.decode_host(rx.cpu().pin_memory(), mask.cpu().pin_memory())
+    ref = orc.decode(code, _np(rx), flags, max_iter=50)
+    assert np.array_equal(h_out.numpy(), ref["out"]) and np.array_equal(h_fail.numpy(), ref["fail_sys"])
+    info = _rand_info(600, codec.k, 64, seed=21)
+    h_cw = codec.encode_host(info.cpu().pin_memory())
+    assert np.array_equal(h_cw.numpy(), orc.encode(code, _np(info)))
+
+
+def test_large_batch_round_trip_properties(codecs):
+    """Full-size style check that does not need the oracle: encode -> erase -> decode returns the input wherever
+    the decoder reports success; decoding is idempotent; XOR-linearity of the encoder."""
+    from ldpc_erasure_codes_b200.codec import LdpcCodec
+    codec = LdpcCodec(code=1, symbol_bytes=64, device=0, max_batch=16384)
+    B = 20000
+    a = _rand_info(B, codec.k, 64, seed=1)
+    b = _rand_info(B, codec.k, 64, seed=2)
+    ca, cb = codec.encode(a), codec.encode(b)
+    assert bool((codec.encode(a ^ b) == (ca ^ cb)).all())
+    rx = ca.clone()
+    mask = codec.gen_erasures(B, 5, P=12, payload=rx)
+    out, fail = codec.decode(rx, mask)
+    good = fail == 0
+    assert 0.9 < float(good.float().mean()) <= 1.0
+    assert bool((out[good] == a[good]).all())
+    out2, fail2 = codec.decode(rx, mask)
+    assert bool((out2 == out).all()) and bool((fail2 == fail).all())
+    codec.close()
