@@ -261,7 +261,7 @@ def run_b200(args):
     barrier()
     clocks = sampler.stop()
     ms_total = ev0.elapsed_time(ev1)
-    launches = sum(v["launches"] for v in codec.profile_read(reset=True).values())
+    launches = sum(v["launches"] for v in codec.profile_read(reset=True).values() if isinstance(v, dict))
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -162,6 +162,10 @@ enum { LDPC_K_PEEL = 0, LDPC_K_EXEC_DECODE = 1, LDPC_K_EXEC_ENCODE = 2, LDPC_K_H
 typedef struct ldpc_profile {
     double ms[LDPC_K_KINDS];        /* summed device time per kernel kind (profiling on)  */
     int64_t launches[LDPC_K_KINDS]; /* kernel launches per kind since create / last reset */
+    /* tuning aid, filled only when the context was created with LDPC_CUDA_PHASE_TIMING=1 in the
+     * environment: SM cycles the executor's group leaders spent per phase, summed over units:
+     * [0] claim + TMA issue, [1] waiting for the load, [2] XOR, [3] store, [4] number of units   */
+    uint64_t exec_phase_cycles[8];
 } ldpc_profile;
 int ldpc_profile_enable(ldpc_ctx *ctx, int on);
 int ldpc_profile_read(ldpc_ctx *ctx, ldpc_profile *out, int reset);

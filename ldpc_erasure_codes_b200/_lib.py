@@ -44,7 +44,7 @@ KIND_NAMES = ["peel", "exec_decode", "exec_encode", "hybrid", "channel", "k5", "
 
 
 class Profile(C.Structure):
-    _fields_ = [("ms", C.c_double * K_KINDS), ("launches", C.c_int64 * K_KINDS)]
+    _fields_ = [("ms", C.c_double * K_KINDS), ("launches", C.c_int64 * K_KINDS), ("exec_phase_cycles", C.c_uint64 * 8)]
 
 
 _lib = None

@@ -147,7 +147,9 @@ class LdpcCodec:
     def profile_read(self, reset=True):
         p = _lib.Profile()
         _lib.check(self.lib.ldpc_profile_read(self._h, C.byref(p), 1 if reset else 0))
-        return {name: dict(ms=p.ms[i], launches=p.launches[i]) for i, name in enumerate(_lib.KIND_NAMES)}
+        d = {name: dict(ms=p.ms[i], launches=p.launches[i]) for i, name in enumerate(_lib.KIND_NAMES)}
+        d["exec_phase_cycles"] = list(p.exec_phase_cycles)
+        return d
 
 
 def fill_random(t: torch.Tensor, seed: int, block0: int = 0):

@@ -133,6 +133,7 @@ struct ldpc_ctx {
     uint32_t *d_resid = nullptr;
     uint8_t *d_fail_scratch = nullptr;
     unsigned long long *d_stats = nullptr;
+    unsigned long long *d_phase = nullptr;   // LDPC_CUDA_PHASE_TIMING=1
     // geometry
     ExecGeom dec, enc;
     int force_W = 0, force_slots = 0;
@@ -190,7 +191,7 @@ static int choose_geom(const ldpc_ctx *c, bool dynamic_sched, ExecGeom *g)
     const int n = c->code.n, S = c->S;
     const int cidx_bytes = c->code.m * c->code.RW * 2;
     const int blob = sched_blob_max_bytes(c->code.m);
-    const int fixed = cidx_bytes + 2 * 8 * 8 + 256;
+    const int fixed = cidx_bytes + 128 + 128 + 64 + 128 + 128;
     ExecGeom best;
     for (int W = std::min(S, 64); W >= 16; W >>= 1) {
         if (S % W) continue;
@@ -204,7 +205,7 @@ static int choose_geom(const ldpc_ctx *c, bool dynamic_sched, ExecGeom *g)
         if (nslot < 1) continue;
         ExecGeom cand;
         cand.W = W; cand.nslot = nslot; cand.slot_bytes = slot; cand.sched_area = blob;
-        cand.smem_bytes = nslot * slot + (dynamic_sched ? nslot : 1) * blob + cidx_bytes + 2 * 8 * 8 + 64;
+        cand.smem_bytes = nslot * slot + (dynamic_sched ? nslot : 1) * blob + cidx_bytes + 128 + 128 + 64 + 128;
         if (!best.W || (best.nslot < 3 && cand.nslot > best.nslot)) best = cand;
         if (best.nslot >= 3) break;
     }
@@ -218,7 +219,7 @@ static void free_ctx(ldpc_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaFree(c->d_cidx); cudaFree(c->d_vadj); cudaFree(c->d_enc_blob); cudaFree(c->d_sched);
-    cudaFree(c->d_sched_len); cudaFree(c->d_resid); cudaFree(c->d_stats); cudaFree(c->d_fail_scratch);
+    cudaFree(c->d_sched_len); cudaFree(c->d_resid); cudaFree(c->d_stats); cudaFree(c->d_fail_scratch); cudaFree(c->d_phase);
     hybrid_free(c->hyb);
     for (auto &r : c->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (int i = 0; i < 2; i++) {
@@ -331,6 +332,12 @@ extern "C" int ldpc_ctx_create(ldpc_ctx **out, const char *h_mat_path, int code_
     CTX_TRY(cudaMalloc(&c->d_fail_scratch, size_t(max_batch)));
     CTX_TRY(cudaMalloc(&c->d_stats, 8 * sizeof(unsigned long long)));
     CTX_TRY(cudaMemset(c->d_stats, 0, 8 * sizeof(unsigned long long)));
+    if (const char *e = getenv("LDPC_CUDA_PHASE_TIMING")) {
+        if (*e && *e != '0') {
+            CTX_TRY(cudaMalloc(&c->d_phase, 8 * sizeof(unsigned long long)));
+            CTX_TRY(cudaMemset(c->d_phase, 0, 8 * sizeof(unsigned long long)));
+        }
+    }
 #undef CTX_TRY
     rc = choose_geom(c, true, &c->dec);
     if (!rc) rc = choose_geom(c, false, &c->enc);
@@ -424,6 +431,7 @@ static int launch_exec(ldpc_ctx *c, const ExecGeom &g, const void *d_in, int row
     p.sched_max = g.sched_area; p.m = c->code.m; p.RW = c->code.RW; p.rows_in = rows_in; p.rows_out = rows_out;
     p.nbox_in = (rows_in + kBoxRows - 1) / kBoxRows; p.nbox_out = (rows_out + kBoxRows - 1) / kBoxRows;
     p.slices = c->S / g.W; p.nslot = g.nslot; p.slot_bytes = g.slot_bytes;
+    p.phase_cycles = sched_stride ? c->d_phase : nullptr;
     int rwm = 0;
     ExecKernel k = pick_exec(g.W, c->code.max_row_weight, &rwm);
     if (!k || (rwm + 7) / 8 * 8 != c->code.RW) return fail(LDPC_ERR_UNSUPPORTED, "no executor instantiation for this slice width / row weight");
@@ -628,6 +636,10 @@ extern "C" int ldpc_profile_read(ldpc_ctx *c, ldpc_profile *out, int reset)
         if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) out->ms[r.kind] += ms;
     }
     for (int i = 0; i < LDPC_K_KINDS; i++) out->launches[i] = c->launches[i];
+    if (c->d_phase) {
+        CUDA_TRY(cudaMemcpy(out->exec_phase_cycles, c->d_phase, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        if (reset) CUDA_TRY(cudaMemset(c->d_phase, 0, 8 * sizeof(unsigned long long)));
+    }
     if (reset) {
         for (auto &r : c->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
         c->prof_recs.clear();

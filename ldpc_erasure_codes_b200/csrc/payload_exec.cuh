@@ -45,11 +45,23 @@ struct ExecParams {
     int slices;                 // S / W
     int nslot;                  // = number of warp groups
     int slot_bytes;             // shared bytes per slot
+    unsigned long long *phase_cycles;  // tuning aid (nullptr = off): [0] claim+issue, [1] load wait, [2] XOR, [3] store, [4] units
 };
 
 __device__ __forceinline__ void xor_acc(uint4 &a, const uint4 v)
 {
     a.x ^= v.x; a.y ^= v.y; a.z ^= v.z; a.w ^= v.w;
+}
+
+__device__ __forceinline__ uint4 lds128(uint32_t addr)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4 v)
+{
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
 template <int W, int RWM>  // W = slice bytes; RWM = members gathered per check (>= max row weight)
@@ -69,7 +81,7 @@ payload_exec_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
     uint16_t *cidx_s = reinterpret_cast<uint16_t *>(blobs + size_t(dynamic ? p.nslot : 1) * p.sched_max);
     uint64_t *full = reinterpret_cast<uint64_t *>(cidx_s + size_t(p.m) * (RWQ * 8));   // [nslot]
     uint8_t *zrow = reinterpret_cast<uint8_t *>(full + 8);   // 64 zero bytes: what a skipped member reads
-    int *mailbox = reinterpret_cast<int *>(zrow + 64);       // [g] unit of group g, [8] next-unit counter
+    int *mailbox = reinterpret_cast<int *>(zrow + 64);       // [g] unit of group g, [8] next unit, [16 + g] level hand-off
 
     const int g = threadIdx.x / GT;          // group = slot
     const int tg = threadIdx.x % GT;         // thread in group
@@ -100,85 +112,146 @@ payload_exec_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
     const int n_units = int(cw_per_cta * p.slices);
 
     uint8_t *slot = slots + size_t(g) * p.slot_bytes;
-    uint8_t *base = slot + (tg % LPG) * 16;
-    const uint8_t *zero = zrow + (tg % LPG) * 16;
+    const uint32_t base_a = smem_u32(slot) + (tg % LPG) * 16;    // shared-space addresses
+    const uint32_t zero_a = smem_u32(zrow) + (tg % LPG) * 16;
     uint8_t *blob = blobs + (dynamic ? size_t(g) * p.sched_max : 0);
-    const int eg = tg / LPG;                 // entry lane-group inside the warp group
     const int bar_id = 1 + g;
+    const uint32_t done_a = smem_u32(&mailbox[16 + g]);          // per-group "level workers done" counter
     uint32_t phase = 0;
 
+    // leader state: the next unit is claimed (and its blob length fetched) one unit ahead, so that the
+    // global-memory latency of that read is off the critical path
+    int j_next = 0;
+    uint32_t blen_next = 0;
+    auto claim = [&]() {
+        j_next = atomicAdd(&mailbox[8], 1);
+        blen_next = 0;
+        if (dynamic && j_next < n_units)
+            blen_next = p.sched_len[blockIdx.x + (long long)(j_next / p.slices) * gridDim.x];
+    };
+    if (leader) claim();
+    long long t_prev = p.phase_cycles ? clock64() : 0;
+    auto lap = [&](int phase_id) {   // leader-only phase timer
+        if (p.phase_cycles && leader) {
+            const long long t = clock64();
+            atomicAdd(&p.phase_cycles[phase_id], (unsigned long long)(t - t_prev));
+            t_prev = t;
+        }
+    };
     while (true) {
-        // ---- leader: claim a unit, start its loads ---------------------------------------
+        // ---- leader: start the loads of the unit claimed earlier, claim the one after -----------
         if (leader) {
-            const int j = atomicAdd(&mailbox[8], 1);
+            const int j = j_next;
             mailbox[g] = j;
+            mailbox[16 + g] = 0;
             if (j < n_units) {
                 const long long b = blockIdx.x + (long long)(j / p.slices) * gridDim.x;
                 const int sl = j % p.slices;
-                uint32_t bytes = uint32_t(p.nbox_in) * kBoxRows * W;
-                uint32_t blen = 0;
-                if (dynamic) { blen = p.sched_len[b]; bytes += blen; }
-                mbar_arrive_expect_tx(&full[g], bytes);
+                const uint32_t blen = blen_next;
+                mbar_arrive_expect_tx(&full[g], uint32_t(p.nbox_in) * kBoxRows * W + blen);
                 for (int i = 0; i < p.nbox_in; i++)
                     tma_load_3d(slot + size_t(i) * kBoxRows * W, &in_map, sl * W, i * kBoxRows, int(b), &full[g]);
                 if (dynamic) bulk_load_1d(blob, p.sched + b * (long long)p.sched_stride, blen, &full[g]);
+                claim();
             }
         }
         named_bar_sync(bar_id, GT);
         const int j = mailbox[g];
         if (j >= n_units) break;
+        lap(0);
         mbar_wait(&full[g], phase);
         phase ^= 1u;
+        lap(1);
 
         // ---- XOR the schedule into the slot -----------------------------------------------
+        // The level walk is a chain of shared-memory round trips (a level's gathers cannot start
+        // before the previous level's results are written, ~500 cycles per level all told), so:
+        //  * everything that does NOT depend on the payload -- which entry a lane group handles
+        //    next, the check's member list, the members' shared addresses -- is prepared ahead;
+        //  * consecutive small levels go to different warps of the group (entry slots rotate by one
+        //    warp per level), and there is NO group-wide barrier between levels: a warp that finishes
+        //    its part of level l bumps a completion counter (release) and goes on to prepare its next
+        //    task; a warp about to execute level L spins (acquire) until the counter shows that all
+        //    workers of the levels below are done.
         const uint32_t *hdr = reinterpret_cast<const uint32_t *>(blob);
         const int ne = int(hdr[0]);
         const int nl = int(hdr[1]);
         const uint32_t *ent = hdr + 4;
         const uint16_t *lvo = reinterpret_cast<const uint16_t *>(ent + ne);
-        // software pipeline: the entry word and its check row for the NEXT level are fetched
-        // before the barrier that ends the current level (they do not depend on the payload)
-        int e1 = nl > 0 ? int(lvo[1]) : 0;
-        int i = eg;                                   // my first entry of level 0 (starts at 0)
-        uint32_t e = 0;
-        uint32_t rr[RWQ * 4];
-        auto fetch = [&](int idx) {
-            e = ent[idx];
+        constexpr int EPW = 32 / LPG;                 // entries per warp and pass
+        constexpr int WPGc = kExecWarpsPerGroup;
+        const int wg = tg >> 5;                       // warp in group
+        const int es = (tg & 31) / LPG;               // entry slot inside the warp
+        int t_idx = 0, t_end = 0;
+        bool t_valid = false;
+        uint32_t t_dst = 0;
+        uint32_t t_src[RWM];
+        auto prepare = [&]() {                        // member addresses of entry t_idx
+            const uint32_t e = ent[t_idx];
+            const uint32_t v = e & 0xFFFFu;
             const uint4 *row = reinterpret_cast<const uint4 *>(cidx_s + size_t(e >> 16) * (RWQ * 8));
+            uint32_t rr[RWQ * 4];
 #pragma unroll
             for (int qq = 0; qq < RWQ; qq++) {
                 const uint4 r4 = row[qq];
                 rr[qq * 4 + 0] = r4.x; rr[qq * 4 + 1] = r4.y; rr[qq * 4 + 2] = r4.z; rr[qq * 4 + 3] = r4.w;
             }
-        };
-        if (i < e1) fetch(i);
-        for (int l = 0; l < nl; l++) {
-            while (i < e1) {
-                const uint32_t v = e & 0xFFFFu;
-                uint4 val[RWM];
 #pragma unroll
-                for (int t = 0; t < RWM; t++) {
-                    const uint32_t u = (rr[t >> 1] >> ((t & 1) * 16)) & 0xFFFFu;
-                    const uint8_t *src = (u == v || u == 0xFFFFu) ? zero : base + size_t(u) * W;
-                    val[t] = *reinterpret_cast<const uint4 *>(src);
-                }
-                uint4 acc = val[0];
-#pragma unroll
-                for (int t = 1; t < RWM; t++) xor_acc(acc, val[t]);
-                *reinterpret_cast<uint4 *>(base + size_t(v) * W) = acc;
-                i += NGROUPS;
-                if (i < e1) fetch(i);
+            for (int t = 0; t < RWM; t++) {
+                const uint32_t u = (t & 1) ? (rr[t >> 1] >> 16) : (rr[t >> 1] & 0xFFFFu);
+                t_src[t] = (u == v || u == 0xFFFFu) ? zero_a : base_a + u * W;
             }
-            const int e0n = e1;                       // next level
-            if (l + 1 < nl) e1 = int(lvo[l + 2]);
-            i = e0n + eg;
-            if (l + 1 < nl && i < e1) fetch(i);
-            named_bar_sync(bar_id, GT);
+            t_dst = base_a + v * W;
+        };
+        auto works = [&](int l, int cnt) { return ((wg + l) % WPGc) * EPW < cnt; };
+        auto setup = [&](int l) {                     // my lane group's first entry in level l (my warp works there)
+            const int s0 = lvo[l];
+            t_end = lvo[l + 1];
+            t_idx = s0 + ((wg + l) % WPGc) * EPW + es;
+            t_valid = t_idx < t_end;
+            if (t_valid) prepare();
+        };
+        int prepared_lvl = -1;
+        uint32_t done_target = 0;                     // workers of all levels below the current one
+        for (int l = 0; l < nl; l++) {
+            const int cnt = int(lvo[l + 1]) - int(lvo[l]);
+            const int nw = min(WPGc, (cnt + EPW - 1) / EPW);
+            if (works(l, cnt)) {
+                if (prepared_lvl != l) setup(l);
+                if (done_target) {                    // wait for the levels below
+                    uint32_t seen;
+                    do {
+                        asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(seen) : "r"(done_a) : "memory");
+                    } while (seen < done_target);
+                }
+                while (t_valid) {
+                    uint4 val[RWM];
+#pragma unroll
+                    for (int t = 0; t < RWM; t++) val[t] = lds128(t_src[t]);
+#pragma unroll
+                    for (int st = 1; st < RWM; st <<= 1)           // XOR tree
+#pragma unroll
+                        for (int t = 0; t + st < RWM; t += 2 * st) xor_acc(val[t], val[t + st]);
+                    sts128(t_dst, val[0]);
+                    t_idx += NGROUPS;                  // another pass in this level?
+                    t_valid = t_idx < t_end;
+                    if (t_valid) prepare();
+                }
+                __syncwarp();
+                if ((tg & 31) == 0)
+                    asm volatile("red.release.cta.shared::cta.add.u32 [%0], %1;" ::"r"(done_a), "r"(1u) : "memory");
+                // off the critical path: find my warp's next level and prepare its first pass
+                for (int l2 = l + 1; l2 < nl; l2++) {
+                    if (works(l2, int(lvo[l2 + 1]) - int(lvo[l2]))) { setup(l2); prepared_lvl = l2; break; }
+                }
+            }
+            done_target += uint32_t(nw);
         }
 
         // ---- store the first rows_out rows, recycle the slot --------------------------------
         fence_proxy_async_smem();
         named_bar_sync(bar_id, GT);
+        lap(2);
         if (leader) {
             const long long b = blockIdx.x + (long long)(j / p.slices) * gridDim.x;
             const int sl = j % p.slices;
@@ -187,6 +260,8 @@ payload_exec_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
             bulk_commit();
             bulk_wait_read0();   // the slot's bytes are on their way to L2; it may be overwritten now
         }
+        lap(3);
+        if (p.phase_cycles && leader) atomicAdd(&p.phase_cycles[4], 1ull);
     }
     if (leader) bulk_wait_all0();
 }
