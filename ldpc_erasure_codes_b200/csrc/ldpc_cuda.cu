@@ -390,7 +390,7 @@ extern "C" int ldpc_ctx_set_exec_geometry(ldpc_ctx *c, int slice_bytes, int slot
 // ------------------------------------------------------------------------------------------
 // executor launch
 // ------------------------------------------------------------------------------------------
-typedef void (*ExecKernel)(const CUtensorMap, const CUtensorMap, const ExecParams);
+typedef void (*ExecKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const ExecParams);
 
 // instantiated member counts: 7 / 14 are the committed codes' maximum row weights
 static ExecKernel pick_exec(int W, int max_row_weight, int *rwm_out)
@@ -418,15 +418,18 @@ static ExecKernel pick_exec(int W, int max_row_weight, int *rwm_out)
 
 static int launch_exec(ldpc_ctx *c, const ExecGeom &g, const void *d_in, int rows_in, void *d_out, int rows_out,
                        const uint8_t *sched, const uint32_t *sched_len, int sched_stride, long long B,
-                       cudaStream_t st)
+                       cudaStream_t st, void *d_full = nullptr)
 {
     if (B <= 0) return LDPC_OK;
-    CUtensorMap in_map, out_map;
+    CUtensorMap in_map, out_map, full_map;
     int rc = make_map(&in_map, d_in, c->S, rows_in, B, g.W, true);
     if (rc) return rc;
     rc = make_map(&out_map, d_out, c->S, rows_out, B, g.W, false);
     if (rc) return rc;
+    rc = make_map(&full_map, d_full ? d_full : d_in, c->S, rows_in, B, g.W, false);
+    if (rc) return rc;
     ExecParams p;
+    p.store_full = d_full ? 1 : 0;
     p.cidx = c->d_cidx; p.sched = sched; p.sched_len = sched_len; p.B = B; p.sched_stride = sched_stride;
     p.sched_max = g.sched_area; p.m = c->code.m; p.RW = c->code.RW; p.rows_in = rows_in; p.rows_out = rows_out;
     p.nbox_in = (rows_in + kBoxRows - 1) / kBoxRows; p.nbox_out = (rows_out + kBoxRows - 1) / kBoxRows;
@@ -440,7 +443,7 @@ static int launch_exec(ldpc_ctx *c, const ExecGeom &g, const void *d_in, int row
     const int grid = int(std::min<long long>(c->num_sms, B));
     {
         ProfScope ps(c, sched_stride ? LDPC_K_EXEC_DECODE : LDPC_K_EXEC_ENCODE, st);
-        k<<<grid, g.nslot * kExecWarpsPerGroup * 32, g.smem_bytes, st>>>(in_map, out_map, p);
+        k<<<grid, g.nslot * kExecWarpsPerGroup * 32, g.smem_bytes, st>>>(in_map, out_map, full_map, p);
     }
     CUDA_TRY(cudaGetLastError());
     return debug_sync(sched_stride ? "payload_exec_kernel(decode)" : "payload_exec_kernel(encode)", st);
@@ -554,6 +557,13 @@ static int decode_chunk(ldpc_ctx *c, const uint8_t *d_cw, const uint32_t *d_mask
     pp.RW = c->code.RW; pp.VW = c->code.VW; pp.NW = c->NW; pp.MW = c->MW; pp.stride = c->sched_stride;
     pp.max_iter = max_iter; pp.rs_n = c->rs_n; pp.rs_k = c->rs_k; pp.groups_per_block = c->peel_groups;
     pp.count_stats = 1;
+    pp.ge_list = nullptr; pp.ge_count = nullptr;
+    if (mode == LDPC_MODE_HYBRID) {
+        int rch = hybrid_prepare(c->hyb, c->code, c->S, c->NW, c->MW, c->num_sms, c->smem_optin, c->max_batch, g_err);
+        if (rch) return rch;
+        CUDA_TRY(cudaMemsetAsync(c->hyb.d_count, 0, 4, st));
+        pp.ge_list = c->hyb.d_list; pp.ge_count = c->hyb.d_count;
+    }
     const int grid = int(std::min<long long>(c->num_sms, (B + c->peel_groups - 1) / c->peel_groups));
     {
         ProfScope ps(c, LDPC_K_PEEL, st);
@@ -561,12 +571,21 @@ static int decode_chunk(ldpc_ctx *c, const uint8_t *d_cw, const uint32_t *d_mask
     }
     CUDA_TRY(cudaGetLastError());
     { int rcd = debug_sync("peel_schedule_kernel", st); if (rcd) return rcd; }
-    int rc = launch_exec(c, c->dec, d_cw, c->code.n, d_out, c->code.k, c->d_sched, c->d_sched_len, c->sched_stride, B, st);
+    int rc = launch_exec(c, c->dec, d_cw, c->code.n, d_out, c->code.k, c->d_sched, c->d_sched_len, c->sched_stride, B, st,
+                         mode == LDPC_MODE_HYBRID ? c->hyb.d_full : nullptr);
     if (rc) return rc;
     if (mode == LDPC_MODE_HYBRID) {
-        rc = hybrid_stage(c->hyb, c->code, c->d_cidx, c->S, c->num_sms, c->smem_optin, d_cw, d_mask, c->d_sched,
-                          c->sched_stride, c->d_resid, d_out, pp.fail, c->d_stats, B, c->max_batch, st, g_err);
-        if (rc) return rc;
+        GeParams gp;
+        gp.mask = d_mask; gp.sched = c->d_sched; gp.list = c->hyb.d_list; gp.list_count = c->hyb.d_count;
+        gp.full = c->hyb.d_full; gp.out = d_out; gp.fail = pp.fail; gp.stats = c->d_stats; gp.cidx = c->d_cidx;
+        gp.gmat = c->hyb.d_gmat; gp.n = c->code.n; gp.k = c->code.k; gp.m = c->code.m; gp.RW = c->code.RW; gp.NW = c->NW;
+        gp.MW = c->MW; gp.S = c->S; gp.stride = c->sched_stride; gp.RSW = c->hyb.RSW;
+        {
+            ProfScope ps(c, LDPC_K_HYBRID, st);
+            hybrid_ge_kernel<<<c->hyb.grid, kGeThreads, c->hyb.smem, st>>>(gp);
+        }
+        CUDA_TRY(cudaGetLastError());
+        { int rcd = debug_sync("hybrid_ge_kernel", st); if (rcd) return rcd; }
     }
     return LDPC_OK;
 }

@@ -45,6 +45,7 @@ struct ExecParams {
     int slices;                 // S / W
     int nslot;                  // = number of warp groups
     int slot_bytes;             // shared bytes per slot
+    int store_full;             // hybrid mode: units whose codeword still has erasures also store all rows_in rows to full_map
     unsigned long long *phase_cycles;  // tuning aid (nullptr = off): [0] claim+issue, [1] load wait, [2] XOR, [3] store, [4] units
 };
 
@@ -67,7 +68,7 @@ __device__ __forceinline__ void sts128(uint32_t addr, const uint4 v)
 template <int W, int RWM>  // W = slice bytes; RWM = members gathered per check (>= max row weight)
 __global__ void __launch_bounds__(kExecMaxGroups *kExecWarpsPerGroup * 32, 1)
 payload_exec_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap out_map,
-                    const ExecParams p)
+                    const __grid_constant__ CUtensorMap full_map, const ExecParams p)
 {
     constexpr int RWQ = (RWM + 7) / 8;                // uint4 chunks of a padded check row
     constexpr int LPG = W / 16;                       // lanes per entry
@@ -257,6 +258,9 @@ payload_exec_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
             const int sl = j % p.slices;
             for (int q = 0; q < p.nbox_out; q++)
                 tma_store_3d(&out_map, slot + size_t(q) * kBoxRows * W, sl * W, q * kBoxRows, int(b));
+            if (p.store_full && reinterpret_cast<const uint32_t *>(blob)[2] != 0u)   // erasures left: the elimination stage
+                for (int q = 0; q < p.nbox_in; q++)                                   // needs every recovered symbol
+                    tma_store_3d(&full_map, slot + size_t(q) * kBoxRows * W, sl * W, q * kBoxRows, int(b));
             bulk_commit();
             bulk_wait_read0();   // the slot's bytes are on their way to L2; it may be overwritten now
         }

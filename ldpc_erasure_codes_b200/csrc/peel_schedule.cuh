@@ -42,6 +42,8 @@ struct PeelParams {
     const uint16_t *vadj;       // [n][VW]
     long long B;
     int n, k, m, RW, VW, NW, MW, stride, max_iter, rs_n, rs_k, groups_per_block, count_stats;
+    unsigned int *ge_list;      // hybrid mode: codewords that still have erasures are appended here ...
+    unsigned int *ge_count;     // ... (nullptr otherwise)
 };
 
 constexpr int kPeelG = 8;
@@ -295,6 +297,7 @@ __global__ void __launch_bounds__(1024) peel_schedule_kernel(const PeelParams p)
             p.sched_len[cw] = (16u + 4u * ne + 2u * (nl + 1u) + 15u) & ~15u;
             if (p.fail) p.fail[cw] = rem_sys > 0 ? 1 : 0;
             if (p.resid) p.resid[cw] = uint32_t(n_er);
+            if (p.ge_list && n_er > 0) p.ge_list[atomicAdd(p.ge_count, 1u)] = (unsigned int)cw;
             my_frames++;
             if (rem_sys > 0) my_fail++;
         }

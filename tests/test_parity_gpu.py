@@ -238,3 +238,75 @@ def test_large_batch_round_trip_properties(codecs):
     out2, fail2 = codec.decode(rx, mask)
     assert bool((out2 == out).all()) and bool((fail2 == fail).all())
     codec.close()
+
+
+# ------------------------------------------------------------------------------- hybrid-ML (GF(2) elimination)
+def _hybrid_check(codec, code, rx, mask, flags, max_iter=10):
+    codec.reset_stats()
+    out, fail = codec.decode(rx, mask, max_iter=max_iter, mode="hybrid")
+    st = codec.stats()
+    ref = orc.decode(code, _np(rx), flags, max_iter=max_iter, mode="hybrid")
+    assert np.array_equal(_np(fail), ref["fail_sys"])
+    assert np.array_equal(_np(out), ref["out"])
+    assert st["ml_attempts"] == int((ref["status"] > 0).sum())
+    assert st["ml_failures"] == int((ref["status"] == 2).sum())
+    return ref
+
+
+@pytest.mark.parametrize("P", [10, 12, 13, 14, 16])
+def test_hybrid_decode_bit_exact(codecs, P):
+    """Matlab/My_LDPC_HybridML_Erasure_Decoder.m: 10 sweeps, then elimination on the residual set."""
+    codec = codecs(1, 64)
+    code, cw, rx, mask, flags = _scenario(codec, 1, 160, P, 500 + P, 64)
+    ref = _hybrid_check(codec, code, rx, mask, flags)
+    good = ref["fail_sys"] == 0
+    assert np.array_equal(ref["out"][good], _np(cw)[good][:, :code.k])
+    if P == 13:
+        assert (ref["status"] == 1).sum() > 20      # the elimination stage really ran and succeeded
+
+
+def test_hybrid_survey_frames(codecs):
+    """(2040,1530), P=13/64, seed 12345: frame 0 (447 erasures) and frame 2 need elimination."""
+    codec = codecs(1, 16)
+    code = orc.Code.builtin(1)
+    v = (np.arange(1, code.k + 1, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15)).view(np.uint8).reshape(code.k, 8)
+    info = torch.from_numpy(np.tile(np.tile(v, (1, 2))[None], (3, 1, 1)).copy()).cuda()
+    cw = codec.encode(info)
+    rx = cw.clone()
+    mask = codec.gen_erasures(3, 12345, P=13, payload=rx)
+    flags = orc.gen_erasures_iid(code.n, 12345, 3, P=13)
+    assert list(flags.sum(axis=1)) == [447, 387, 432]
+    out, fail = codec.decode(rx, mask, max_iter=10, mode="hybrid")
+    assert not _np(fail).any() and np.array_equal(_np(out), _np(info))
+    # the same frames from the peeling fixed point (cap not binding) give the same unique answer
+    out2, fail2 = codec.decode(rx, mask, max_iter=1000, mode="hybrid")
+    assert np.array_equal(_np(out2), _np(info))
+
+
+@pytest.mark.parametrize("S", [16, 128])
+def test_hybrid_other_symbol_sizes(codecs, S):
+    codec = codecs(1, S)
+    code, cw, rx, mask, flags = _scenario(codec, 1, 60, 13, 77, S)
+    _hybrid_check(codec, code, rx, mask, flags)
+
+
+def test_hybrid_n2000_global_workspace(codecs):
+    codec = codecs(0, 64)
+    code, cw, rx, mask, flags = _scenario(codec, 0, 40, 27, 5, 64)     # 42 %: beyond the peeling threshold
+    ref = _hybrid_check(codec, code, rx, mask, flags)
+    assert (ref["status"] > 0).any()
+
+
+def test_hybrid_n4000_bursty_stress(codecs):
+    """Config 3: n4000/k2000 under the two-state channel, parameters that do reach stopping sets."""
+    from ldpc_erasure_codes_b200.codec import unpack_mask
+    codec = codecs(2, 64)
+    code = orc.Code.builtin(2)
+    B = 10
+    info = _rand_info(B, codec.k, 64, seed=3)
+    cw = codec.encode(info)
+    rx = cw.clone()
+    mask = codec.gen_erasures(B, 2024, bursty=(0.38, 0.9, 10.0), payload=rx)
+    flags = unpack_mask(mask, code.n)
+    ref = _hybrid_check(codec, code, rx, mask, flags)
+    assert (ref["status"] > 0).any()
