@@ -82,7 +82,7 @@ def load():
     lib.rs_decode.argtypes = [vp, vp, vp, vp, vp, i64, vp]
     lib.ldpc_last_error_string.restype = C.c_char_p
     lib.ldpc_cuda_abi_version.restype = i32
-    for name in EXPORTS:
+    for name in EXPORTS:  # every entry point returns an int status except the error string
         fn = getattr(lib, name)
         if name not in ("ldpc_last_error_string",):
             fn.restype = i32

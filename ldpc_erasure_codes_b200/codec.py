@@ -174,3 +174,55 @@ def pack_mask(flags):
     pad = np.zeros((B, nw * 32), np.uint8)
     pad[:, :n] = flags
     return np.packbits(pad, axis=1, bitorder="little").view(np.uint32).astype(np.int32, copy=False).reshape(B, nw)
+
+
+class RsCodec:
+    """Reed-Solomon GF(2^8) erasure codec (rs_ctx): field 0x171, G[i][j] = alpha^(i*j) systematised,
+    decode from the first k received symbols -- Matlab/ReedSolomonErasureCodes.m, Test_My_RS_Decode.m."""
+
+    def __init__(self, n=255, k=191, symbol_bytes=1024, device=0, max_batch=4096):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("RsCodec needs a CUDA device (sm_100a); there is no CPU fallback")
+        h = C.c_void_p()
+        _lib.check(self.lib.rs_ctx_create(C.byref(h), n, k, symbol_bytes, device, max_batch))
+        self._h = h
+        self.n, self.k, self.S = n, k, symbol_bytes
+        self.mask_words = (n + 31) // 32
+        self.device = torch.device("cuda", device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.rs_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def generator(self):
+        g = np.zeros((self.k, self.n), np.uint8)
+        _lib.check(self.lib.rs_ctx_get_generator(self._h, g.ctypes.data_as(C.c_void_p)))
+        return g
+
+    def encode(self, info: torch.Tensor, out=None):
+        assert info.is_cuda and info.dtype == torch.uint8 and info.is_contiguous()
+        B = info.shape[0]
+        assert info.shape[1:] == (self.k, self.S)
+        if out is None:
+            out = torch.empty((B, self.n, self.S), dtype=torch.uint8, device=info.device)
+        _lib.check(self.lib.rs_encode(self._h, _ptr(info), _ptr(out), B, _stream()))
+        return out
+
+    def decode(self, cw: torch.Tensor, mask: torch.Tensor, out=None, fail=None):
+        assert cw.is_cuda and cw.dtype == torch.uint8 and cw.is_contiguous() and mask.is_contiguous()
+        B = cw.shape[0]
+        assert cw.shape[1:] == (self.n, self.S) and mask.shape == (B, self.mask_words)
+        if out is None:
+            out = torch.empty((B, self.k, self.S), dtype=torch.uint8, device=cw.device)
+        if fail is None:
+            fail = torch.empty((B,), dtype=torch.uint8, device=cw.device)
+        _lib.check(self.lib.rs_decode(self._h, _ptr(cw), _ptr(mask), _ptr(out), _ptr(fail), B, _stream()))
+        return out, fail

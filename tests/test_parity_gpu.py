@@ -310,3 +310,67 @@ def test_hybrid_n4000_bursty_stress(codecs):
     flags = unpack_mask(mask, code.n)
     ref = _hybrid_check(codec, code, rx, mask, flags)
     assert (ref["status"] > 0).any()
+
+
+# ------------------------------------------------------------------------------- Reed-Solomon GF(256)
+@pytest.fixture(scope="module")
+def rs_codecs():
+    from ldpc_erasure_codes_b200.codec import RsCodec
+    cache = {}
+
+    def get(n, k, S):
+        if (n, k, S) not in cache:
+            cache[(n, k, S)] = RsCodec(n=n, k=k, symbol_bytes=S, device=0, max_batch=256)
+        return cache[(n, k, S)]
+    yield get
+    for c in cache.values():
+        c.close()
+
+
+@pytest.mark.parametrize("nk", [(255, 191), (255, 192), (250, 125), (7, 5)])
+def test_rs_generator_matches_oracle(rs_codecs, nk):
+    n, k = nk
+    assert np.array_equal(rs_codecs(n, k, 16).generator(), orc.rs_gsys(n, k))
+
+
+@pytest.mark.parametrize("n,k,S", [(255, 191, 1024), (255, 192, 64), (7, 5, 16)])
+def test_rs_encode_bit_exact(rs_codecs, n, k, S):
+    codec = rs_codecs(n, k, S)
+    info = _rand_info(5, k, S, seed=n + k)
+    cw = _np(codec.encode(info))
+    G = orc.rs_gsys(n, k)
+    for b in range(5):
+        assert np.array_equal(cw[b], orc.rs_encode(G, _np(info)[b]))
+
+
+@pytest.mark.parametrize("n,k,S,p", [(255, 191, 1024, 0.2), (255, 192, 64, 0.2), (255, 191, 64, 0.05), (7, 5, 16, 0.25)])
+def test_rs_decode_bit_exact(rs_codecs, n, k, S, p):
+    """Decoder == restated Matlab/My_RS_Decode_Optimize_With_GFTables.m on the first k received symbols."""
+    from ldpc_erasure_codes_b200.codec import pack_mask
+    codec = rs_codecs(n, k, S)
+    B = 24
+    rng = np.random.default_rng(n * 7 + k)
+    info = _rand_info(B, k, S, seed=k)
+    cw = codec.encode(info)
+    flags = (rng.random((B, n)) < p).astype(np.uint8)
+    flags[0] = 0                                  # nothing erased
+    flags[1] = 0; flags[1, :n - k] = 1            # exactly n - k systematic symbols erased: still decodable
+    flags[2] = 0; flags[2, :n - k + 1] = 1        # one too many: undecodable
+    flags[3] = 0; flags[3, k:] = 1                # all repair symbols erased
+    rx = _np(cw).copy()
+    rx[flags == 1] = 0
+    out, fail = codec.decode(torch.from_numpy(rx).cuda(), torch.from_numpy(pack_mask(flags)).cuda())
+    out, fail = _np(out), _np(fail)
+    G = orc.rs_gsys(n, k)
+    for b in range(B):
+        rec = np.nonzero(flags[b] == 0)[0]
+        if len(rec) >= k:
+            ref, rd = orc.rs_decode(G, rec[:k].astype(np.int32), rx[b][rec[:k]])
+            assert rd == 0 and fail[b] == 0
+            assert np.array_equal(out[b], ref) and np.array_equal(ref, _np(info)[b])
+        else:
+            assert fail[b] == 1
+            want = _np(info)[b].copy()
+            want[flags[b, :k] == 1] = 0
+            assert np.array_equal(out[b], want)
+    assert fail[2] == 1 and fail[1] == 0
