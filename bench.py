@@ -76,7 +76,8 @@ def cpu_decode_rate(S, P, seed, seconds, max_iter, mode="peel"):
     from oracle import oracle as orc
 
     code = orc.Code.builtin(CODE_IND)
-    threads = orc.num_threads()
+    # all host threads this process may use (torchrun exports OMP_NUM_THREADS=1: ask explicitly)
+    threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     rng = np.random.default_rng(seed)
 
     def make(B, frame0):
@@ -89,13 +90,13 @@ def cpu_decode_rate(S, P, seed, seconds, max_iter, mode="peel"):
     # calibrate on a small batch, then size the sample for ~`seconds` of CPU work
     cw, flags = make(64 * threads, 0)
     t0 = time.perf_counter()
-    orc.decode(code, cw, flags, max_iter=max_iter, mode=mode, inplace=True)
+    orc.decode(code, cw, flags, max_iter=max_iter, mode=mode, inplace=True, nthreads=threads)
     dt = time.perf_counter() - t0
     rate = 64 * threads / dt
     B = int(max(64 * threads, min(rate * seconds, 262144)))
     cw, flags = make(B, 1 << 20)
     t0 = time.perf_counter()
-    orc.decode(code, cw, flags, max_iter=max_iter, mode=mode, inplace=True)
+    orc.decode(code, cw, flags, max_iter=max_iter, mode=mode, inplace=True, nthreads=threads)
     dt = time.perf_counter() - t0
     gbps = B * code.k * S * 8 / dt / 1e9
     return gbps, threads, f"{B} codewords n2040/k1530 S={S} P={P}/64, reference sweep decoder, early stop", B, dt
@@ -193,6 +194,7 @@ def run_b200(args):
     import torch
     import torch.distributed as dist
 
+    from ldpc_erasure_codes_b200 import sharding
     from ldpc_erasure_codes_b200.codec import LdpcCodec, fill_random
 
     rank = int(os.environ.get("RANK", "0"))
@@ -221,7 +223,7 @@ def run_b200(args):
     out = torch.empty((resident, sub, k, S), dtype=torch.uint8, device=dev)
     fail = torch.empty((resident, sub), dtype=torch.uint8, device=dev)
     info = torch.empty((sub, k, S), dtype=torch.uint8, device=dev)
-    frame_base = rank * codewords          # global frame index: results do not depend on the sharding
+    frame_base = sharding.weak_frame_base(codewords, rank)   # global frame index: results do not depend on the sharding
     for r in range(resident):
         fill_random(info, seed=args.seed, block0=(frame_base + r * sub) * k * S // 16)
         codec.encode(info, out=rx[r])
@@ -248,6 +250,7 @@ def run_b200(args):
     good = fail[0] == 0
     assert bool((out[0][good] == info[good]).all()), "round-trip check failed on the bench data"
     fer = float(fail.float().mean().item())
+    codec.reset_stats()
     codec.profile_read(reset=True)
 
     sampler = ClockSampler(local_rank)
@@ -262,10 +265,8 @@ def run_b200(args):
     clocks = sampler.stop()
     ms_total = ev0.elapsed_time(ev1)
     launches = sum(v["launches"] for v in codec.profile_read(reset=True).values() if isinstance(v, dict))
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = float(t.item()) / args.steps
+    job_stats = sharding.reduce_stats(codec.stats())             # the reference's ERROR_STAT counters, summed over ranks
+    ms_step = sharding.reduce_max(ms_total) / args.steps      # slowest rank, device-timed
     value = world * codewords * k * S * 8 / (ms_step * 1e-3) / 1e9
 
     # ---- per-kernel device time (separate pass with event brackets around each launch) ---
@@ -287,7 +288,8 @@ def run_b200(args):
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get("payload_exec_decode_dram_bytes_per_launch")
+            per_cw = json.load(f).get("payload_exec_decode_dram_bytes_per_codeword")
+            traffic = per_cw * sub if per_cw else None      # ncu capture of a smaller launch, scaled per codeword
     except Exception:
         pass
 
@@ -311,10 +313,7 @@ def run_b200(args):
             codec.decode_host(h_cw, h_mask, max_iter=args.max_iter, mode=args.mode, out=h_out, fail=h_fail)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt.item())
+        dt = sharding.reduce_max(dt)
         e2e = {"value": world * eb * args.steps * k * S * 8 / dt / 1e9, "unit": "Gbit/s",
                "h2d_bytes_per_step": eb * (n * S + codec.mask_words * 4), "d2h_bytes_per_step": eb * (k * S + 1),
                "codewords_per_step": eb, "api": "ldpc_decode_host (pinned host buffers)"}
@@ -330,13 +329,14 @@ def run_b200(args):
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {
-                "workload": "n2040_k1530 irregular H, 64-byte symbols, 13/64 (20.3%) i.i.d. erasures, "
-                            "1Mi codewords per GPU per step, peel decode" if args.mode == "peel" else "hybrid decode",
+                "workload": f"n2040_k1530 irregular H, {S}-byte symbols, {P}/64 ({100 * P / 64:.1f}%) i.i.d. erasures, "
+                            f"{codewords} codewords per GPU per step, {args.mode} decode",
                 "symbol_bytes": S, "per64": P, "max_iter": args.max_iter, "mode": args.mode,
                 "codewords_per_gpu_per_step": codewords, "sub_batch": sub, "resident_sub_batches": resident,
                 "l2": "every launch reads a distinct 8.5 GB sub-batch (>> 126 MB L2), no flush needed",
                 "slice_bytes": codec.info.slice_bytes, "exec_slots": codec.info.exec_slots,
                 "frame_error_rate": fer, "parallelism": f"codeword-sharded x{world}, no collectives",
+                "counters": job_stats,
             },
             "roofline": {"bound": "hbm", "kernel": "payload_exec_kernel(decode)", "achieved": achieved, "peak": peak,
                          "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
