@@ -30,7 +30,7 @@
 
 namespace ldpc {
 
-constexpr int kGeThreads = 256;
+constexpr int kGeThreads = 512;
 
 struct GeParams {
     const uint32_t *mask;            // [B][NW] erasure masks as received
@@ -52,6 +52,7 @@ __host__ __device__ inline size_t ge_small_bytes(int m, int NW)
     return size_t(NW) * 4 + size_t(NW + 1) * 4 + 260 * 4 + size_t(m) * 2 * 2 + size_t(m) * 2 + 64 + 64;
 }
 
+template <bool GMAT>   // where [A | I] lives: per-CTA global workspace (true) or shared memory (false)
 __global__ void __launch_bounds__(kGeThreads) hybrid_ge_kernel(const GeParams p)
 {
     extern __shared__ __align__(16) uint8_t ge_smem[];
@@ -70,7 +71,7 @@ __global__ void __launch_bounds__(kGeThreads) hybrid_ge_kernel(const GeParams p)
     uint8_t *used = reinterpret_cast<uint8_t *>(pivrow + m);
     uint8_t *inv = used + m;
     uint32_t *mat_s = reinterpret_cast<uint32_t *>((reinterpret_cast<uintptr_t>(inv + m) + 15) & ~uintptr_t(15));
-    uint32_t *mat = p.gmat ? p.gmat + size_t(blockIdx.x) * m * RSW : mat_s;
+    uint32_t *mat = GMAT ? p.gmat + size_t(blockIdx.x) * m * RSW : mat_s;
 
     const unsigned int count = *p.list_count;
     for (unsigned int li = blockIdx.x; li < count; li += gridDim.x) {
@@ -139,11 +140,18 @@ __global__ void __launch_bounds__(kGeThreads) hybrid_ge_kernel(const GeParams p)
                 for (int i = tid; i < RSW; i += kGeThreads) prow[i] = mat[size_t(piv) * RSW + i];
                 if (tid == 0) { used[piv] = 1; pivrow[col] = uint16_t(piv); }
                 __syncthreads();
-                for (int r = warp; r < m; r += kGeThreads / 32) {
-                    if (r == piv || !inv[r]) continue;
-                    uint32_t *row = mat + size_t(r) * RSW;
-                    if (row[cwrd] & cbit)
-                        for (int i = lane; i < RSW; i += 32) row[i] ^= prow[i];
+                // rows are tested 32 at a time (one per lane, ballot), then each row that has the bit is
+                // updated by the whole warp, one matrix word per lane
+                for (int r0 = warp * 32; r0 < m; r0 += kGeThreads) {
+                    const int r = r0 + lane;
+                    const bool hit = r < m && r != piv && inv[r] && (mat[size_t(r) * RSW + cwrd] & cbit);
+                    unsigned todo = __ballot_sync(0xFFFFFFFFu, hit);
+                    while (todo) {
+                        const int rr = r0 + __ffs(todo) - 1;
+                        todo &= todo - 1u;
+                        uint32_t *row = mat + size_t(rr) * RSW;
+                        for (int i = lane; i < 2 * MW; i += 32) row[i] ^= prow[i];   // (word 2*MW is padding)
+                    }
                 }
                 __syncthreads();
             }
@@ -237,7 +245,9 @@ inline int hybrid_prepare(HybridScratch &h, const HostCode &code, int S, int NW,
         h.grid = num_sms;
         if ((e = cudaMalloc(&h.d_gmat, size_t(h.grid) * mat)) != cudaSuccess) return bad("hybrid: matrix workspace", e);
     }
-    if ((e = cudaFuncSetAttribute(hybrid_ge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(budget))) != cudaSuccess)
+    if ((e = cudaFuncSetAttribute(hybrid_ge_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(budget))) != cudaSuccess)
+        return bad("hybrid: cudaFuncSetAttribute", e);
+    if ((e = cudaFuncSetAttribute(hybrid_ge_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(budget))) != cudaSuccess)
         return bad("hybrid: cudaFuncSetAttribute", e);
     h.ready = true;
     return LDPC_OK;

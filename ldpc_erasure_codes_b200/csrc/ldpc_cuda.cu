@@ -582,7 +582,8 @@ static int decode_chunk(ldpc_ctx *c, const uint8_t *d_cw, const uint32_t *d_mask
         gp.MW = c->MW; gp.S = c->S; gp.stride = c->sched_stride; gp.RSW = c->hyb.RSW;
         {
             ProfScope ps(c, LDPC_K_HYBRID, st);
-            hybrid_ge_kernel<<<c->hyb.grid, kGeThreads, c->hyb.smem, st>>>(gp);
+            if (gp.gmat) hybrid_ge_kernel<true><<<c->hyb.grid, kGeThreads, c->hyb.smem, st>>>(gp);
+            else hybrid_ge_kernel<false><<<c->hyb.grid, kGeThreads, c->hyb.smem, st>>>(gp);
         }
         CUDA_TRY(cudaGetLastError());
         { int rcd = debug_sync("hybrid_ge_kernel", st); if (rcd) return rcd; }
