@@ -46,7 +46,7 @@ struct PeelParams {
     unsigned int *ge_count;     // ... (nullptr otherwise)
 };
 
-constexpr int kPeelG = 8;
+constexpr int kPeelG = 8;          // lanes per codeword (4 codewords per warp, in lockstep); 4 was measured slower
 constexpr uint32_t kFired = 31u;
 
 // per-codeword shared words: state[m] | cur[BMW] | nxt[BMW] | msk[NW + 1] + 3 scratch words, each 4-word aligned
@@ -69,26 +69,29 @@ __device__ __forceinline__ int popc_range(const uint32_t *w, int lo, int hi)  //
     return cnt;
 }
 
-__device__ __forceinline__ int group_sum(int v)  // over the 8 lanes of a group (xor < 8 stays inside it)
+template <int G>
+__device__ __forceinline__ int group_sum(int v)  // over the G lanes of a group (xor < G stays inside it)
 {
-    v += __shfl_xor_sync(0xFFFFFFFFu, v, 4);
-    v += __shfl_xor_sync(0xFFFFFFFFu, v, 2);
-    v += __shfl_xor_sync(0xFFFFFFFFu, v, 1);
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
     return v;
 }
+template <int G>
 __device__ __forceinline__ uint32_t group_max(uint32_t v)
 {
-    v = max(v, __shfl_xor_sync(0xFFFFFFFFu, v, 4));
-    v = max(v, __shfl_xor_sync(0xFFFFFFFFu, v, 2));
-    v = max(v, __shfl_xor_sync(0xFFFFFFFFu, v, 1));
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
     return v;
 }
 
-template <int WPL, int VW>   // WPL = bitmap words per lane (2, 4, 8); VW = padded variable degree (4, 8)
+template <int BMW, int VW>   // BMW = bitmap words per codeword (16, 32, 64); VW = padded variable degree (4, 8)
 __global__ void __launch_bounds__(1024) peel_schedule_kernel(const PeelParams p)
 {
     constexpr int G = kPeelG;
-    constexpr int BMW = G * WPL;              // bitmap words per codeword
+    constexpr int WPL = BMW / G;              // bitmap words scanned per lane (a multiple of 4)
+    constexpr int NPL = (VW + G - 1) / G;     // neighbour checks handled per lane
+    constexpr unsigned GMASK = (1u << G) - 1u;
+    static_assert(WPL == 2 || WPL % 4 == 0, "bitmap words per lane are read with 64- or 128-bit loads");
     constexpr unsigned FULL = 0xFFFFFFFFu;
     extern __shared__ __align__(16) uint32_t sh[];
     __shared__ unsigned int s_stat[4];
@@ -126,7 +129,7 @@ __global__ void __launch_bounds__(1024) peel_schedule_kernel(const PeelParams p)
     const int msk_off = bmb_off + BMW;
     const int LC = 2 * BMW + NW;              // level counters that fit in the dead bitmap/mask area
     const int lc_off = bma_off;
-    const int dummy_off = msk_off + NW + 1 + lane % 3;   // scratch words behind the mask 
+    const int dummy_off = msk_off + NW + 1 + lane % 3;     // (distinct lanes may share a scratch word: values are never read back)   // scratch words behind the mask 
 
     unsigned int my_fail = 0, my_rs = 0, my_frames = 0;
     const long long stride = (long long)gridDim.x * p.groups_per_block;
@@ -148,8 +151,8 @@ __global__ void __launch_bounds__(1024) peel_schedule_kernel(const PeelParams p)
         }
 #pragma unroll
         for (int i = 0; i < 2 * WPL; i++) sh[bma_off + lane + i * G] = 0u;
-        n_er = group_sum(n_er);
-        rem_sys = group_sum(rem_sys);
+        n_er = group_sum<G>(n_er);
+        rem_sys = group_sum<G>(rem_sys);
         __syncwarp();
         if (p.count_stats && p.rs_n > 0 && valid) {  // RS-equivalent MDS counting, perf_tests.cl:70-80
             for (int b = lane; b < p.n / p.rs_n; b += G)
@@ -187,7 +190,7 @@ __global__ void __launch_bounds__(1024) peel_schedule_kernel(const PeelParams p)
             uint32_t xs[WPL];
             if (WPL == 2) {
                 const uint2 t = *reinterpret_cast<const uint2 *>(&sh[cur_off + lane * 2]);
-                xs[0] = t.x; xs[1] = t.y;
+                xs[0] = t.x; xs[WPL - 1] = t.y;
             } else {
 #pragma unroll
                 for (int q = 0; q < WPL / 4; q++) {
@@ -199,9 +202,9 @@ __global__ void __launch_bounds__(1024) peel_schedule_kernel(const PeelParams p)
 #pragma unroll
             for (int i = WPL - 1; i >= 0; i--)
                 if (xs[i]) myc = ((lane * WPL + i) << 5) + __ffs(xs[i]) - 1;
-            const unsigned gb = (__ballot_sync(FULL, myc >= 0) >> gshift) & 0xFFu;
+            const unsigned gb = (__ballot_sync(FULL, myc >= 0) >> gshift) & GMASK;
             const int src = __ffs(gb) - 1;                                   // -1: nothing pending
-            const int c = __shfl_sync(FULL, myc, gshift + (src & 7));        // (src = -1 reads a lane whose myc is -1)
+            const int c = __shfl_sync(FULL, myc, gshift + (src & (G - 1)));  // (src = -1 reads a lane whose myc is -1)
             // Straight-line, select-based body: the four codewords of the warp take the same
             // instruction path whatever they do this step (pop / stale pop / end of sweep / idle).
             const bool pop = active && c >= 0;
@@ -214,16 +217,20 @@ __global__ void __launch_bounds__(1024) peel_schedule_kernel(const PeelParams p)
             ne += fire ? 1u : 0u;
             n_er -= fire ? 1 : 0;
             rem_sys -= (fire && int(v) < p.k) ? 1 : 0;
-            const uint32_t c2 = (lane < VW) ? vadj_s[v * VW + lane] : 0xFFFFu;
-            const bool upd = fire && c2 != 0xFFFFu;
-            const int a2 = upd ? state_off + int(c2) : dummy_off;        // idle lanes hit a scratch word
-            const uint32_t s2 = sh[a2];
-            const uint32_t cnt2 = (s2 >> 27) - 1u;
-            const uint32_t l2 = max((s2 >> 16) & 0x7FFu, lvl);
-            const bool self = int(c2) == c;
-            sh[a2] = self ? ((kFired << 27) | (lvl << 16) | v) : ((cnt2 << 27) | (l2 << 16) | ((s2 & 0xFFFFu) ^ v));
-            if (upd && !self && cnt2 == 1u)
-                atomicOr(&sh[(int(c2) > c ? cur_off : nxt_off) + (c2 >> 5)], 1u << (c2 & 31));
+#pragma unroll
+            for (int t = 0; t < NPL; t++) {
+                const int j = lane * NPL + t;
+                const uint32_t c2 = (j < VW) ? vadj_s[v * VW + j] : 0xFFFFu;
+                const bool upd = fire && c2 != 0xFFFFu;
+                const int a2 = upd ? state_off + int(c2) : dummy_off;        // idle lanes hit a scratch word
+                const uint32_t s2 = sh[a2];
+                const uint32_t cnt2 = (s2 >> 27) - 1u;
+                const uint32_t l2 = max((s2 >> 16) & 0x7FFu, lvl);
+                const bool self = int(c2) == c;
+                sh[a2] = self ? ((kFired << 27) | (lvl << 16) | v) : ((cnt2 << 27) | (l2 << 16) | ((s2 & 0xFFFFu) ^ v));
+                if (upd && !self && cnt2 == 1u)
+                    atomicOr(&sh[(int(c2) > c ? cur_off : nxt_off) + (c2 >> 5)], 1u << (c2 & 31));
+            }
             // end of sweep: swap the bitmaps; stop at the cap or at the fixed point (two empty sweeps)
             sweep += swp ? 1 : 0;
             const int t_off = cur_off;
@@ -246,12 +253,12 @@ __global__ void __launch_bounds__(1024) peel_schedule_kernel(const PeelParams p)
                 nl = max(nl, L);
             }
         }
-        nl = group_max(nl);
+        nl = group_max<G>(nl);
         __syncwarp();
         uint8_t *blob = p.sched + (valid ? cw : 0) * (long long)p.stride;
         uint32_t *g_ent = reinterpret_cast<uint32_t *>(blob) + 4;
         uint16_t *g_off = reinterpret_cast<uint16_t *>(g_ent + ne);
-        const unsigned gm = 0xFFu << gshift;
+        const unsigned gm = GMASK << gshift;
         if (int(nl) < LC) {
             uint32_t run = 0;  // exclusive scan over levels 1..nl, G at a time
             for (uint32_t base = 1; base <= nl; base += G) {
@@ -284,7 +291,7 @@ __global__ void __launch_bounds__(1024) peel_schedule_kernel(const PeelParams p)
                     const int c = c0 + lane;
                     const uint32_t st = (c < m) ? sh[state_off + c] : 0u;
                     const bool hit = (st >> 27) == kFired && ((st >> 16) & 0x7FFu) == L;
-                    const unsigned hb = (__ballot_sync(gm, hit) >> gshift) & 0xFFu;
+                    const unsigned hb = (__ballot_sync(gm, hit) >> gshift) & GMASK;
                     if (hit) g_ent[run + __popc(hb & ((1u << lane) - 1u))] = (st & 0xFFFFu) | (uint32_t(c) << 16);
                     run += __popc(hb);
                 }
