@@ -234,8 +234,8 @@ typedef void (*PeelKernel)(const PeelParams);
 static PeelKernel pick_peel(int MW, int VW)
 {
     const int bmw = peel_bitmap_words(MW);
-    if (VW == 4) return bmw == 16 ? peel_schedule_kernel<2, 4> : (bmw == 32 ? peel_schedule_kernel<4, 4> : peel_schedule_kernel<8, 4>);
-    if (VW == 8) return bmw == 16 ? peel_schedule_kernel<2, 8> : (bmw == 32 ? peel_schedule_kernel<4, 8> : peel_schedule_kernel<8, 8>);
+    if (VW == 4) return bmw == 16 ? peel_schedule_kernel<16, 4> : (bmw == 32 ? peel_schedule_kernel<32, 4> : peel_schedule_kernel<64, 4>);
+    if (VW == 8) return bmw == 16 ? peel_schedule_kernel<16, 8> : (bmw == 32 ? peel_schedule_kernel<32, 8> : peel_schedule_kernel<64, 8>);
     return nullptr;
 }
 
