@@ -35,8 +35,8 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-N_CODE, K_CODE = 2040, 1530
-CODE_IND = 1
+CODE_IND = 1          # BASELINE.json's metric is quoted on (2040,1530); -c selects another built-in code
+CODE_NAMES = {0: "n2000_k1000 triangular H", 1: "n2040_k1530 irregular H", 2: "n4000_k2000 triangular H"}
 
 
 def parse_args():
@@ -46,11 +46,13 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--symbol-bytes", type=int, default=64)
-    ap.add_argument("--per64", type=int, default=13, help="erasure rate numerator / 64 (reference flag -p)")
-    ap.add_argument("--codewords", type=int, default=1 << 20, help="codewords per GPU per step")
+    # the reference host's own flags (main.cpp:157-170): -p PER numerator / 64, -n frames, -i iterations, -c code
+    ap.add_argument("-p", "--per64", type=int, default=13, help="erasure rate numerator / 64 (reference flag -p)")
+    ap.add_argument("-n", "--codewords", type=int, default=1 << 20, help="codewords (frames) per GPU per step (reference flag -n)")
     ap.add_argument("--sub-batch", type=int, default=1 << 16)
     ap.add_argument("--resident", type=int, default=8, help="distinct sub-batches kept in HBM")
-    ap.add_argument("--max-iter", type=int, default=50)
+    ap.add_argument("-i", "--max-iter", type=int, default=50, help="sweeps over the checks (reference flag -i, default 50)")
+    ap.add_argument("-c", "--code", type=int, default=1, help="0 = (2000,1000), 1 = (2040,1530) [the benchmark], 2 = (4000,2000)")
     ap.add_argument("--mode", default="peel", choices=["peel", "hybrid"])
     ap.add_argument("--e2e-batch", type=int, default=1 << 15)
     ap.add_argument("--seed", type=int, default=12345)
@@ -99,7 +101,7 @@ def cpu_decode_rate(S, P, seed, seconds, max_iter, mode="peel"):
     orc.decode(code, cw, flags, max_iter=max_iter, mode=mode, inplace=True, nthreads=threads)
     dt = time.perf_counter() - t0
     gbps = B * code.k * S * 8 / dt / 1e9
-    return gbps, threads, f"{B} codewords n2040/k1530 S={S} P={P}/64, reference sweep decoder, early stop", B, dt
+    return gbps, threads, f"{B} codewords {CODE_NAMES[CODE_IND].split()[0]} S={S} P={P}/64, reference sweep decoder, early stop", B, dt
 
 
 def run_reference(args):
@@ -122,7 +124,8 @@ def run_reference(args):
         "impl": "reference", "metric": "decoded info Gbit/s (n2040 k1530, 20% erasures)", "value": v, "unit": "Gbit/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sum(ms) / len(ms),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "n2040_k1530 irregular H, 64-byte symbols, 13/64 (20.3%) i.i.d. erasures, peel decode",
+        "config": {"workload": f"{CODE_NAMES[CODE_IND]}, {args.symbol_bytes}-byte symbols, {args.per64}/64 "
+                               f"({100 * args.per64 / 64:.1f}%) i.i.d. erasures, {args.mode} decode",
                    "symbol_bytes": args.symbol_bytes, "per64": args.per64, "max_iter": args.max_iter, "mode": args.mode},
         "cpu_baseline": {"value": v, "unit": "Gbit/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "Gbit/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -329,7 +332,7 @@ def run_b200(args):
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {
-                "workload": f"n2040_k1530 irregular H, {S}-byte symbols, {P}/64 ({100 * P / 64:.1f}%) i.i.d. erasures, "
+                "workload": f"{CODE_NAMES[CODE_IND]}, {S}-byte symbols, {P}/64 ({100 * P / 64:.1f}%) i.i.d. erasures, "
                             f"{codewords} codewords per GPU per step, {args.mode} decode",
                 "symbol_bytes": S, "per64": P, "max_iter": args.max_iter, "mode": args.mode,
                 "codewords_per_gpu_per_step": codewords, "sub_batch": sub, "resident_sub_batches": resident,
@@ -351,7 +354,9 @@ def run_b200(args):
 
 
 def main():
+    global CODE_IND
     args = parse_args()
+    CODE_IND = args.code
     if args.impl == "reference":
         run_reference(args)
     else:
