@@ -97,6 +97,9 @@ typedef struct ldpc_stats {
     int64_t rs_errors;        /* RS-equivalent blocks beyond MDS capacity           */
     int64_t ml_attempts;      /* hybrid mode: frames that entered GF(2) elimination */
     int64_t ml_failures;      /* hybrid mode: rank-deficient eliminations           */
+    int64_t ml_recovered;     /* hybrid mode: frames counted in ldpc_errors whose systematic
+                                 symbols the elimination then recovered (hybrid frame errors =
+                                 ldpc_errors - ml_recovered)                         */
 } ldpc_stats;
 
 /* ---- context ------------------------------------------------------------------------
@@ -145,6 +148,15 @@ int ldpc_gen_erasures(ldpc_ctx *ctx, const ldpc_erasure_model *model, uint32_t s
  * rank-deficient eliminations.                                                           */
 int ldpc_decode(ldpc_ctx *ctx, const void *d_cw, const uint32_t *d_mask, void *d_out,
                 uint8_t *d_fail, int max_iter, int mode, int64_t B, void *stream);
+
+/* ---- error-rate run ---------------------------------------------------------------
+ * The reference's committed flow in one call (main.cpp:555-659 with decoder_top.cl:57-158 and
+ * ldpc_erasure_decoder_perf_tests.cl): `frames` all-zero codewords get synthetic erasures
+ * (data_in), are decoded (only the erasure pattern matters for an all-zero codeword) and only
+ * the cumulative counters come back (ERROR_STAT / data_out).  Runs the pattern phase only --
+ * no payload is moved -- and ADDS to the context's counters (read them with ldpc_get_stats). */
+int ldpc_simulate_fer(ldpc_ctx *ctx, const ldpc_erasure_model *model, uint32_t seed, uint64_t frame0,
+                      int64_t frames, int max_iter, int mode, void *stream);
 
 /* ---- statistics ---------------------------------------------------------------------
  * Replaces the ERROR_STAT channel + data_out report (decoder_top.cl:123-158).

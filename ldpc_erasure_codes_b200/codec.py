@@ -97,6 +97,25 @@ class LdpcCodec:
                                               _ptr(payload), _stream()))
         return mask
 
+    @staticmethod
+    def _model(P=None, p=None, bursty=None):
+        m = _lib.ErasureModel()
+        if P is not None:
+            m.model, m.per_numerator_div_64 = 0, int(P)
+        elif p is not None:
+            m.model, m.threshold32 = 1, min(int(p * 2 ** 32), 2 ** 32 - 1)
+        else:
+            m.model = 2
+            m.alpha, m.beta, m.bias = bursty
+        return m
+
+    # ---- the reference's committed run: all-zero codewords, counters only -----------------------
+    def simulate_fer(self, frames, seed, P=None, p=None, bursty=None, max_iter=50, mode="peel", frame0=0):
+        """host -c <code> -p <P> -n <frames> -i <max_iter>: adds to the counters read by stats()."""
+        m = self._model(P, p, bursty)
+        _lib.check(self.lib.ldpc_simulate_fer(self._h, C.byref(m), seed & 0xFFFFFFFF, frame0, frames, max_iter,
+                                              {"peel": MODE_PEEL, "hybrid": MODE_HYBRID}[mode], _stream()))
+
     # ---- ldpc_erasure_decoder(num_iter, code_ind) + data_out ----------------------------
     def decode(self, cw: torch.Tensor, mask: torch.Tensor, max_iter=50, mode="peel", out=None, fail=None):
         assert cw.is_cuda and cw.dtype == torch.uint8 and cw.is_contiguous() and mask.is_contiguous()

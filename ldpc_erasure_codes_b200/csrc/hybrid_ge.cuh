@@ -40,7 +40,7 @@ struct GeParams {
     const uint8_t *full;             // [B][n][S] every symbol after peeling (valid for listed codewords)
     uint8_t *out;                    // [B][k][S]
     uint8_t *fail;                   // [B]
-    unsigned long long *stats;       // [3] ml_attempts, [4] ml_failures
+    unsigned long long *stats;       // [3] ml_attempts, [4] ml_failures, [5] ml_recovered
     const uint16_t *cidx;            // [m][RW]
     uint32_t *gmat;                  // per-CTA global workspace for [A | I], or nullptr (shared memory)
     int n, k, m, RW, NW, MW, S, stride;
@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(kGeThreads) hybrid_ge_kernel(const GeParams p)
             }
         }
         // ---- 4. payload: syndromes, then every erased systematic symbol -----------------------
-        if (ok) {
+        if (ok && p.full) {   // (full == nullptr: error-rate run, pattern only)
             const uint8_t *full = p.full + size_t(cw) * p.n * p.S;
             uint8_t *out = p.out + size_t(cw) * p.k * p.S;
             const int qd = tid & 3;             // 16-byte quarter of a 64-byte chunk
@@ -196,8 +196,12 @@ __global__ void __launch_bounds__(kGeThreads) hybrid_ge_kernel(const GeParams p)
         }
         if (tid == 0) {
             atomicAdd(&p.stats[3], 1ull);
-            if (ok) { if (p.fail) p.fail[cw] = 0; }
-            else atomicAdd(&p.stats[4], 1ull);
+            if (ok) {
+                if (p.fail) p.fail[cw] = 0;
+                if (hdr[3] != 0u) atomicAdd(&p.stats[5], 1ull);   // a frame the peel kernel counted as an error
+            } else {
+                atomicAdd(&p.stats[4], 1ull);
+            }
         }
         __syncthreads();
     }

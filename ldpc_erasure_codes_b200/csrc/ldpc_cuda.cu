@@ -134,6 +134,7 @@ struct ldpc_ctx {
     uint8_t *d_fail_scratch = nullptr;
     unsigned long long *d_stats = nullptr;
     unsigned long long *d_phase = nullptr;   // LDPC_CUDA_PHASE_TIMING=1
+    uint32_t *d_sim_mask = nullptr;          // ldpc_simulate_fer: masks of one chunk
     // geometry
     ExecGeom dec, enc;
     int force_W = 0, force_slots = 0;
@@ -219,7 +220,7 @@ static void free_ctx(ldpc_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaFree(c->d_cidx); cudaFree(c->d_vadj); cudaFree(c->d_enc_blob); cudaFree(c->d_sched);
-    cudaFree(c->d_sched_len); cudaFree(c->d_resid); cudaFree(c->d_stats); cudaFree(c->d_fail_scratch); cudaFree(c->d_phase);
+    cudaFree(c->d_sched_len); cudaFree(c->d_resid); cudaFree(c->d_stats); cudaFree(c->d_fail_scratch); cudaFree(c->d_phase); cudaFree(c->d_sim_mask);
     hybrid_free(c->hyb);
     for (auto &r : c->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (int i = 0; i < 2; i++) {
@@ -571,13 +572,16 @@ static int decode_chunk(ldpc_ctx *c, const uint8_t *d_cw, const uint32_t *d_mask
     }
     CUDA_TRY(cudaGetLastError());
     { int rcd = debug_sync("peel_schedule_kernel", st); if (rcd) return rcd; }
-    int rc = launch_exec(c, c->dec, d_cw, c->code.n, d_out, c->code.k, c->d_sched, c->d_sched_len, c->sched_stride, B, st,
-                         mode == LDPC_MODE_HYBRID ? c->hyb.d_full : nullptr);
-    if (rc) return rc;
+    const bool pattern_only = d_cw == nullptr;   // error-rate run: no payload
+    if (!pattern_only) {
+        int rc = launch_exec(c, c->dec, d_cw, c->code.n, d_out, c->code.k, c->d_sched, c->d_sched_len, c->sched_stride, B, st,
+                             mode == LDPC_MODE_HYBRID ? c->hyb.d_full : nullptr);
+        if (rc) return rc;
+    }
     if (mode == LDPC_MODE_HYBRID) {
         GeParams gp;
         gp.mask = d_mask; gp.sched = c->d_sched; gp.list = c->hyb.d_list; gp.list_count = c->hyb.d_count;
-        gp.full = c->hyb.d_full; gp.out = d_out; gp.fail = pp.fail; gp.stats = c->d_stats; gp.cidx = c->d_cidx;
+        gp.full = pattern_only ? nullptr : c->hyb.d_full; gp.out = d_out; gp.fail = pp.fail; gp.stats = c->d_stats; gp.cidx = c->d_cidx;
         gp.gmat = c->hyb.d_gmat; gp.n = c->code.n; gp.k = c->code.k; gp.m = c->code.m; gp.RW = c->code.RW; gp.NW = c->NW;
         gp.MW = c->MW; gp.S = c->S; gp.stride = c->sched_stride; gp.RSW = c->hyb.RSW;
         {
@@ -612,6 +616,28 @@ extern "C" int ldpc_decode(ldpc_ctx *c, const void *d_cw, const uint32_t *d_mask
 }
 
 // ------------------------------------------------------------------------------------------
+// error-rate run (pattern phase only)
+// ------------------------------------------------------------------------------------------
+extern "C" int ldpc_simulate_fer(ldpc_ctx *c, const ldpc_erasure_model *model, uint32_t seed, uint64_t frame0,
+                                 int64_t frames, int max_iter, int mode, void *stream)
+{
+    if (!c || !model || frames < 0) return fail(LDPC_ERR_ARG, "bad argument to ldpc_simulate_fer");
+    if (mode != LDPC_MODE_PEEL && mode != LDPC_MODE_HYBRID) return fail(LDPC_ERR_ARG, "unknown decode mode");
+    if (max_iter < 0 || max_iter > 1000000) return fail(LDPC_ERR_ARG, "max_iter out of range");
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (!c->d_sim_mask) CUDA_TRY(cudaMalloc(&c->d_sim_mask, size_t(c->max_batch) * c->NW * 4));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    for (long long b0 = 0; b0 < frames; b0 += c->max_batch) {
+        const long long nb = std::min<long long>(c->max_batch, frames - b0);
+        int rc = ldpc_gen_erasures(c, model, seed, frame0 + uint64_t(b0), nb, c->d_sim_mask, nullptr, stream);
+        if (rc) return rc;
+        rc = decode_chunk(c, nullptr, c->d_sim_mask, nullptr, nullptr, max_iter, mode, nb, st);
+        if (rc) return rc;
+    }
+    return LDPC_OK;
+}
+
+// ------------------------------------------------------------------------------------------
 // statistics
 // ------------------------------------------------------------------------------------------
 extern "C" int ldpc_get_stats(ldpc_ctx *c, ldpc_stats *out)
@@ -622,7 +648,7 @@ extern "C" int ldpc_get_stats(ldpc_ctx *c, ldpc_stats *out)
     unsigned long long h[8];
     CUDA_TRY(cudaMemcpy(h, c->d_stats, sizeof(h), cudaMemcpyDeviceToHost));
     out->frames = (int64_t)h[0]; out->ldpc_errors = (int64_t)h[1]; out->rs_errors = (int64_t)h[2];
-    out->ml_attempts = (int64_t)h[3]; out->ml_failures = (int64_t)h[4];
+    out->ml_attempts = (int64_t)h[3]; out->ml_failures = (int64_t)h[4]; out->ml_recovered = (int64_t)h[5];
     return LDPC_OK;
 }
 

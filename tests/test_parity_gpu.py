@@ -374,3 +374,27 @@ def test_rs_decode_bit_exact(rs_codecs, n, k, S, p):
             want[flags[b, :k] == 1] = 0
             assert np.array_equal(out[b], want)
     assert fail[2] == 1 and fail[1] == 0
+
+
+# ------------------------------------------------------------------------------- error-rate run (counters only)
+@pytest.mark.parametrize("mode,max_iter", [("peel", 50), ("hybrid", 10)])
+def test_simulate_fer_matches_explicit_decode_and_oracle(codecs, mode, max_iter):
+    """ldpc_simulate_fer = the reference's committed flow (all-zero codewords, counters only): the same counters as
+    generating the masks, decoding zero payloads explicitly, and as the oracle on those masks."""
+    codec = codecs(1, 16)
+    code = orc.Code.builtin(1)
+    B, seed, P = 700, 424242, 13        # 700 > max_batch 512: chunked, frame counter continues across chunks
+    codec.reset_stats()
+    codec.simulate_fer(B, seed, P=P, max_iter=max_iter, mode=mode)
+    sim = codec.stats()
+    rx = torch.zeros((B, code.n, 16), dtype=torch.uint8, device="cuda")
+    mask = codec.gen_erasures(B, seed, P=P)
+    codec.reset_stats()
+    out, fail = codec.decode(rx, mask, max_iter=max_iter, mode=mode)
+    assert codec.stats() == sim
+    flags = orc.gen_erasures_iid(code.n, seed, B, P=P)
+    ref = orc.decode(code, np.zeros((B, code.n, 16), np.uint8), flags, max_iter=max_iter, mode=mode)
+    assert sim["frames"] == B
+    assert sim["ldpc_errors"] - sim["ml_recovered"] == int(ref["fail_sys"].sum()) == int(_np(fail).sum())
+    assert sim["rs_errors"] == sum(orc.rs_mds_count(code.n, 255, 192, f) for f in flags)
+    assert not _np(out).any()           # the all-zero codeword decodes to zeros
