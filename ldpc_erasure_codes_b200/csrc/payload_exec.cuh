@@ -220,9 +220,13 @@ payload_exec_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
             if (works(l, cnt)) {
                 if (prepared_lvl != l) setup(l);
                 if (done_target) {                    // wait for the levels below
-                    uint32_t seen;
+                    uint32_t seen, spins = 0;
                     do {
                         asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(seen) : "r"(done_a) : "memory");
+                        if (++spins > (1u << 26)) {   // a lost hand-off must trap, not hang the GPU
+                            printf("libldpc_cuda: level hand-off timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+                            __trap();
+                        }
                     } while (seen < done_target);
                 }
                 while (t_valid) {

@@ -14,8 +14,8 @@
 //     E = erased systematic symbols (t of them), R = the first t received repair symbols;
 //     M[a][b] = G_sys[E_b][R_a] is inverted by Gauss-Jordan (t <= n-k), and the decode matrix
 //     D (t x k) over the k used received symbols is formed:  u_E = M^-1 (c_R + P_R^T u_known).
-//   payload part (what the time goes to, ~ t*k*S multiply-accumulates): every thread owns one 32-bit
-//     word (4 payload bytes) of all symbols.  Multiplication by a constant c is bit-sliced over the
+//   payload part (what the time goes to, ~ t*k*S multiply-accumulates): a thread owns one 16-byte
+//     column (four 32-bit words) of all symbols and every fourth output.  Multiplication by a constant c is bit-sliced over the
 //     CONSTANT: x*c = XOR_j bit_j(c) * (x * 2^j); the eight doublings x*2^j of a packed word cost 5 ALU
 //     ops each and are shared by all t outputs, and bit_j(c) is applied as a precomputed 32-bit mask
 //     (table of 8 masks per constant in shared memory, read with two broadcast 128-bit loads), so one
@@ -45,7 +45,7 @@ namespace ldpc {
 
 constexpr int kRsThreads = 256;
 constexpr int kRsMaxT = 128;     // n - k <= 128 (matrix dimensions)
-constexpr int kRsTile = 64;      // outputs accumulated in registers per pass over the inputs
+constexpr int kRsOwn = 16;       // outputs a thread accumulates per pass over the inputs (4 * kRsOwn per CTA pass)
 
 struct RsParams {
     const uint8_t *in;      // decode: [B][n][S] received codewords; encode: [B][k][S] info
@@ -64,7 +64,7 @@ __device__ __forceinline__ uint32_t gf_xtime4(uint32_t x)   // multiply four pac
     return ((x & 0x7F7F7F7Fu) << 1) ^ (((x >> 7) & 0x01010101u) * 0x71u);
 }
 
-__global__ void __launch_bounds__(kRsThreads) rs_codec_kernel(const RsParams p)
+__global__ void __launch_bounds__(kRsThreads, 2) rs_codec_kernel(const RsParams p)
 {
     extern __shared__ __align__(16) uint8_t rs_smem[];
     const int n = p.n, k = p.k, r_ = n - k, S = p.S;
@@ -174,55 +174,69 @@ __global__ void __launch_bounds__(kRsThreads) rs_codec_kernel(const RsParams p)
                 __syncthreads();
             }
         }
-        // ---- payload: every thread owns words w, w + 256, ... of all symbols ------------------------------
+        // ---- payload: thread (u, oq) owns the 16-byte column u of every symbol and the outputs
+        //      b = oq, oq + 4, ... (kRsOwn of them per pass); the masks of a coefficient are shared by
+        //      the four words of the column ------------------------------------------------------------
         const int in_rows = p.encode ? k : n;
         const int out_rows = p.encode ? n : k;
-        const uint32_t *in = reinterpret_cast<const uint32_t *>(p.in + size_t(cw) * in_rows * S);
-        uint32_t *out = reinterpret_cast<uint32_t *>(p.out + size_t(cw) * out_rows * S);
-        const int WS = S / 4;
+        const uint4 *in = reinterpret_cast<const uint4 *>(p.in + size_t(cw) * in_rows * S);
+        uint4 *out = reinterpret_cast<uint4 *>(p.out + size_t(cw) * out_rows * S);
+        const int WS = S / 16;                       // 16-byte columns per symbol
         const int nt = (ok && t > 0) ? t : 0;
-        for (int w = tid; w < WS; w += kRsThreads) {
+        const int oq = tid / (kRsThreads / 4);       // output quarter (warp uniform)
+        for (int u = tid % (kRsThreads / 4); u < WS; u += kRsThreads / 4) {
             if (!p.encode && !ok) {
                 // undecodable: pass the received systematic symbols through, erased ones as zero
                 const uint32_t *mk = p.mask + cw * p.NW;
-                for (int j = 0; j < k; j++) out[size_t(j) * WS + w] = ((mk[j >> 5] >> (j & 31)) & 1u) ? 0u : in[size_t(j) * WS + w];
+                for (int j = oq; j < k; j += 4)
+                    out[size_t(j) * WS + u] = ((mk[j >> 5] >> (j & 31)) & 1u) ? make_uint4(0u, 0u, 0u, 0u) : in[size_t(j) * WS + u];
                 continue;
             }
-          for (int t0 = 0; t0 < (nt > 0 ? nt : 1); t0 += kRsTile) {   // outputs in register tiles of 64
-            uint32_t acc[kRsTile];
+            for (int t0 = 0; t0 < (nt > 0 ? nt : 1); t0 += 4 * kRsOwn) {   // 4 * kRsOwn outputs per pass over the inputs
+                uint4 acc[kRsOwn];
 #pragma unroll
-            for (int b = 0; b < kRsTile; b++) acc[b] = 0u;
-            const int ntile = min(kRsTile, nt - t0);
-            for (int ri = 0; ri < k; ri++) {
-                const int pos = rlist[ri];
-                const uint32_t x0 = in[size_t(pos) * WS + w];
-                if (pos < k && t0 == 0) out[size_t(pos) * WS + w] = x0;   // systematic symbols pass through
-                if (nt == 0) continue;
-                const uint32_t x1 = gf_xtime4(x0), x2 = gf_xtime4(x1), x3 = gf_xtime4(x2), x4 = gf_xtime4(x3);
-                const uint32_t x5 = gf_xtime4(x4), x6 = gf_xtime4(x5), x7 = gf_xtime4(x6);
+                for (int i = 0; i < kRsOwn; i++) acc[i] = make_uint4(0u, 0u, 0u, 0u);
+                for (int ri = 0; ri < k; ri++) {
+                    const int pos = rlist[ri];
+                    const uint4 xv = in[size_t(pos) * WS + u];
+                    if (pos < k && t0 == 0 && oq == 0) out[size_t(pos) * WS + u] = xv;   // systematic symbols pass through
+                    if (nt == 0) continue;
+                    uint32_t x[8][4];
+                    x[0][0] = xv.x; x[0][1] = xv.y; x[0][2] = xv.z; x[0][3] = xv.w;
 #pragma unroll
-                for (int g8 = 0; g8 < kRsTile / 8; g8++) {
-                    if (g8 * 8 < ntile) {
+                    for (int j = 1; j < 8; j++)
 #pragma unroll
-                        for (int bb = 0; bb < 8; bb++) {
-                            const int b = g8 * 8 + bb;
-                            const uint32_t c = D[(t0 + b) * k8 + ri];          // rows >= nt are never read back
-                            const uint4 ma = *reinterpret_cast<const uint4 *>(m8 + c * 8);
-                            const uint4 mb = *reinterpret_cast<const uint4 *>(m8 + c * 8 + 4);
-                            acc[b] ^= (ma.x & x0) ^ (ma.y & x1) ^ (ma.z & x2) ^ (ma.w & x3) ^
-                                      (mb.x & x4) ^ (mb.y & x5) ^ (mb.z & x6) ^ (mb.w & x7);
+                        for (int q = 0; q < 4; q++) x[j][q] = gf_xtime4(x[j - 1][q]);
+#pragma unroll
+                    for (int g4 = 0; g4 < kRsOwn / 4; g4++) {
+                        if (t0 + oq + 16 * g4 < nt) {
+#pragma unroll
+                            for (int ii = 0; ii < 4; ii++) {
+                                const int i = g4 * 4 + ii;
+                                const uint32_t c = D[(t0 + oq + 4 * i) * k8 + ri];   // rows >= nt are never read back
+                                const uint4 ma = *reinterpret_cast<const uint4 *>(m8 + c * 8);
+                                const uint4 mb = *reinterpret_cast<const uint4 *>(m8 + c * 8 + 4);
+                                const uint32_t mm[8] = {ma.x, ma.y, ma.z, ma.w, mb.x, mb.y, mb.z, mb.w};
+#pragma unroll
+                                for (int j = 0; j < 8; j++) {
+                                    acc[i].x ^= mm[j] & x[j][0];
+                                    acc[i].y ^= mm[j] & x[j][1];
+                                    acc[i].z ^= mm[j] & x[j][2];
+                                    acc[i].w ^= mm[j] & x[j][3];
+                                }
+                            }
                         }
                     }
                 }
-            }
 #pragma unroll
-            for (int b = 0; b < kRsTile; b++) {
-                if (b < ntile) {
-                    const int row = p.encode ? (k + t0 + b) : int(elist[t0 + b]);
-                    out[size_t(row) * WS + w] = acc[b];
+                for (int i = 0; i < kRsOwn; i++) {
+                    const int b = t0 + oq + 4 * i;
+                    if (b < nt) {
+                        const int row = p.encode ? (k + b) : int(elist[b]);
+                        out[size_t(row) * WS + u] = acc[i];
+                    }
                 }
             }
-          }
         }
         if (!p.encode && tid == 0 && p.fail) p.fail[cw] = ok ? 0 : 1;
         __syncthreads();
