@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(1024) peel_schedule_kernel(const PeelParams p)
     const int m4 = (m + 3) & ~3;
     const int vadj_words = (p.n * VW) / 2;    // u16 table sizes in 32-bit words
     const int cidx_words = (m * RW) / 2;
-    uint16_t *vadj_s = reinterpret_cast<uint16_t *>(sh);
+    (void)0;
     uint16_t *cidx_s = reinterpret_cast<uint16_t *>(sh + vadj_words);
     const int grp_base = vadj_words + cidx_words;
     const uint32_t padidx = uint32_t(NW) * 32u;   // row padding points at the always-zero word msk[NW]
@@ -129,6 +129,7 @@ __global__ void __launch_bounds__(1024) peel_schedule_kernel(const PeelParams p)
     const int msk_off = bmb_off + BMW;
     const int LC = 2 * BMW + NW;              // level counters that fit in the dead bitmap/mask area
     const int lc_off = bma_off;
+    const uint32_t sh_a = smem_u32(sh);
     const int dummy_off = msk_off + NW + 1 + lane % 3;     // (distinct lanes may share a scratch word: values are never read back)   // scratch words behind the mask 
 
     unsigned int my_fail = 0, my_rs = 0, my_frames = 0;
@@ -180,7 +181,12 @@ __global__ void __launch_bounds__(1024) peel_schedule_kernel(const PeelParams p)
         __syncwarp();
 
         // ---- 3. replay of the serial sweeps, four codewords per warp in lockstep -------
-        int cur_off = bma_off, nxt_off = bmb_off;
+        // (explicit shared-space addresses and PTX accessors keep this loop, the kernel's hot spot, to
+        //  ~90 instructions per step; cur/nxt swap by swapping two address registers)
+        uint32_t cur_a = sh_a + 4u * bma_off, nxt_a = sh_a + 4u * bmb_off;
+        const uint32_t st_a = sh_a + 4u * state_off;
+        const uint32_t dummy_a = sh_a + 4u * dummy_off;
+        const uint32_t vadj_a = sh_a;                       // the variable->check table sits first
         int sweep = 1;
         uint32_t ne = 0;
         bool active = valid && n_er > 0 && p.max_iter > 0;
@@ -189,14 +195,13 @@ __global__ void __launch_bounds__(1024) peel_schedule_kernel(const PeelParams p)
             // lowest pending check of this sweep: lane L owns bitmap words [L*WPL, (L+1)*WPL)
             uint32_t xs[WPL];
             if (WPL == 2) {
-                const uint2 t = *reinterpret_cast<const uint2 *>(&sh[cur_off + lane * 2]);
-                xs[0] = t.x; xs[WPL - 1] = t.y;
+                asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(xs[0]), "=r"(xs[WPL - 1]) : "r"(cur_a + lane * 8u) : "memory");
             } else {
 #pragma unroll
-                for (int q = 0; q < WPL / 4; q++) {
-                    const uint4 t = *reinterpret_cast<const uint4 *>(&sh[cur_off + lane * WPL + q * 4]);
-                    xs[q * 4 + 0] = t.x; xs[q * 4 + 1] = t.y; xs[q * 4 + 2] = t.z; xs[q * 4 + 3] = t.w;
-                }
+                for (int q = 0; q < WPL / 4; q++)
+                    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                                 : "=r"(xs[q * 4 + 0]), "=r"(xs[(q * 4 + 1) % WPL]), "=r"(xs[(q * 4 + 2) % WPL]), "=r"(xs[(q * 4 + 3) % WPL])
+                                 : "r"(cur_a + lane * (WPL * 4u) + q * 16u) : "memory");
             }
             int myc = -1;
 #pragma unroll
@@ -209,8 +214,10 @@ __global__ void __launch_bounds__(1024) peel_schedule_kernel(const PeelParams p)
             // instruction path whatever they do this step (pop / stale pop / end of sweep / idle).
             const bool pop = active && c >= 0;
             const bool swp = active && c < 0;
-            if (pop && lane == src) atomicAnd(&sh[cur_off + (c >> 5)], ~(1u << (c & 31)));
-            const uint32_t st = sh[state_off + (pop ? c : 0)];
+            if (pop && lane == src)
+                asm volatile("red.shared.and.b32 [%0], %1;" ::"r"(cur_a + 4u * (uint32_t(c) >> 5)), "r"(~(1u << (c & 31))) : "memory");
+            uint32_t st;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(st) : "r"(st_a + (pop ? 4u * uint32_t(c) : 0u)) : "memory");
             const bool fire = pop && (st >> 27) == 1u;   // else: its symbol was recovered by an earlier check
             const uint32_t v = fire ? (st & 0xFFFFu) : 0u;
             const uint32_t lvl = ((st >> 16) & 0x7FFu) + 1u;
@@ -220,22 +227,29 @@ __global__ void __launch_bounds__(1024) peel_schedule_kernel(const PeelParams p)
 #pragma unroll
             for (int t = 0; t < NPL; t++) {
                 const int j = lane * NPL + t;
-                const uint32_t c2 = (j < VW) ? vadj_s[v * VW + j] : 0xFFFFu;
+                uint32_t c2 = 0xFFFFu;
+                if (j < VW) {
+                    unsigned short c2h;
+                    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(c2h) : "r"(vadj_a + 2u * (v * VW + j)) : "memory");
+                    c2 = c2h;
+                }
                 const bool upd = fire && c2 != 0xFFFFu;
-                const int a2 = upd ? state_off + int(c2) : dummy_off;        // idle lanes hit a scratch word
-                const uint32_t s2 = sh[a2];
+                const uint32_t a2 = upd ? st_a + 4u * c2 : dummy_a;        // idle lanes hit a scratch word
+                uint32_t s2;
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(s2) : "r"(a2) : "memory");
                 const uint32_t cnt2 = (s2 >> 27) - 1u;
                 const uint32_t l2 = max((s2 >> 16) & 0x7FFu, lvl);
                 const bool self = int(c2) == c;
-                sh[a2] = self ? ((kFired << 27) | (lvl << 16) | v) : ((cnt2 << 27) | (l2 << 16) | ((s2 & 0xFFFFu) ^ v));
+                const uint32_t nv = self ? ((kFired << 27) | (lvl << 16) | v) : ((cnt2 << 27) | (l2 << 16) | ((s2 & 0xFFFFu) ^ v));
+                asm volatile("st.shared.u32 [%0], %1;" ::"r"(a2), "r"(nv) : "memory");
                 if (upd && !self && cnt2 == 1u)
-                    atomicOr(&sh[(int(c2) > c ? cur_off : nxt_off) + (c2 >> 5)], 1u << (c2 & 31));
+                    asm volatile("red.shared.or.b32 [%0], %1;" ::"r"((int(c2) > c ? cur_a : nxt_a) + 4u * (c2 >> 5)), "r"(1u << (c2 & 31)) : "memory");
             }
             // end of sweep: swap the bitmaps; stop at the cap or at the fixed point (two empty sweeps)
             sweep += swp ? 1 : 0;
-            const int t_off = cur_off;
-            cur_off = swp ? nxt_off : cur_off;
-            nxt_off = swp ? t_off : nxt_off;
+            const uint32_t t_a = cur_a;
+            cur_a = swp ? nxt_a : cur_a;
+            nxt_a = swp ? t_a : nxt_a;
             active = active && n_er > 0 && !(swp && (sweep > p.max_iter || prev_empty));
             prev_empty = swp ? true : (pop ? false : prev_empty);
             __syncwarp();
