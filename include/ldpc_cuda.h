@@ -116,6 +116,10 @@ int ldpc_ctx_create(ldpc_ctx **out, const char *h_mat_path, int code_ind, int sy
 /* Replaces cleanup() (main.cpp:668-691). */
 int ldpc_ctx_destroy(ldpc_ctx *ctx);
 int ldpc_ctx_info(const ldpc_ctx *ctx, ldpc_code_info *info);
+/* Host-only: parse a MAT-v5 file holding sparse `H_sparse` (the reference's Matlab/ *.mat) without
+ * touching a GPU.  dims receives {m, n, nnz, triangular(0/1)}; row_ptr / col_idx may be NULL to
+ * query the sizes first, else they must hold m+1 and nnz entries.                                   */
+int ldpc_read_h_file(const char *h_mat_path, int32_t dims[4], int32_t *row_ptr, int32_t *col_idx);
 /* Host copy of H as CSR (row_ptr[m+1], col_idx[nnz], 0-based ascending) = the Vlist rows. */
 int ldpc_ctx_get_csr(const ldpc_ctx *ctx, int32_t *row_ptr, int32_t *col_idx);
 /* Tuning knob for experiments: force the executor's slice width W (16/32/64/...) and slot

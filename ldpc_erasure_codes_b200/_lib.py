@@ -10,7 +10,7 @@ SO_PATH = os.path.join(HERE, "libldpc_cuda.so")
 
 # every symbol include/ldpc_cuda.h declares (tests check the library exports all of them)
 EXPORTS = [
-    "ldpc_ctx_create", "ldpc_ctx_destroy", "ldpc_ctx_info", "ldpc_ctx_get_csr", "ldpc_ctx_set_exec_geometry",
+    "ldpc_ctx_create", "ldpc_ctx_destroy", "ldpc_ctx_info", "ldpc_read_h_file", "ldpc_ctx_get_csr", "ldpc_ctx_set_exec_geometry",
     "ldpc_encode", "ldpc_gen_erasures", "ldpc_decode", "ldpc_simulate_fer", "ldpc_get_stats", "ldpc_reset_stats",
     "ldpc_encode_host", "ldpc_decode_host", "ldpc_fill_random", "ldpc_profile_enable", "ldpc_profile_read",
     "rs_ctx_create", "rs_ctx_destroy", "rs_ctx_get_generator", "rs_encode", "rs_decode",
@@ -63,6 +63,7 @@ def load():
     lib.ldpc_ctx_create.argtypes = [C.POINTER(vp), C.c_char_p, i32, i32, i32, i64]
     lib.ldpc_ctx_destroy.argtypes = [vp]
     lib.ldpc_ctx_info.argtypes = [vp, C.POINTER(CodeInfo)]
+    lib.ldpc_read_h_file.argtypes = [C.c_char_p, C.POINTER(C.c_int32 * 4), vp, vp]
     lib.ldpc_ctx_get_csr.argtypes = [vp, vp, vp]
     lib.ldpc_ctx_set_exec_geometry.argtypes = [vp, i32, i32]
     lib.ldpc_encode.argtypes = [vp, vp, vp, i64, vp]

@@ -171,6 +171,17 @@ class LdpcCodec:
         return d
 
 
+def read_h_file(path: str):
+    """Parse a MAT-v5 code file with the library's own C++ loader (no GPU needed) -> (m, n, triangular, row_ptr, col_idx)."""
+    lib = _lib.load()
+    dims = (C.c_int32 * 4)()
+    _lib.check(lib.ldpc_read_h_file(path.encode(), C.byref(dims), None, None))
+    rp = np.zeros(dims[0] + 1, np.int32)
+    ci = np.zeros(dims[2], np.int32)
+    _lib.check(lib.ldpc_read_h_file(path.encode(), C.byref(dims), rp.ctypes.data_as(C.c_void_p), ci.ctypes.data_as(C.c_void_p)))
+    return dims[0], dims[1], bool(dims[3]), rp, ci
+
+
 def fill_random(t: torch.Tensor, seed: int, block0: int = 0):
     """Counter-based synthetic payload (Threefry key {2, seed}); t must be a CUDA byte tensor."""
     lib = _lib.load()

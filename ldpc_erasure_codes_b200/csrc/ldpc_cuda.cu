@@ -348,6 +348,23 @@ extern "C" int ldpc_ctx_create(ldpc_ctx **out, const char *h_mat_path, int code_
     return LDPC_OK;
 }
 
+extern "C" int ldpc_read_h_file(const char *h_mat_path, int32_t dims[4], int32_t *row_ptr, int32_t *col_idx)
+{
+    if (!h_mat_path || !dims) return fail(LDPC_ERR_ARG, "NULL argument");
+    int rows, cols;
+    std::vector<int32_t> col_ptr, row_idx;
+    std::string err;
+    int rc = load_mat_sparse(h_mat_path, "H_sparse", rows, cols, col_ptr, row_idx, err);
+    if (rc) return fail(rc, err);
+    HostCode code;
+    rc = build_code(rows, cols, col_ptr, row_idx, code, err);
+    if (rc) return fail(rc, err);
+    dims[0] = code.m; dims[1] = code.n; dims[2] = code.nnz; dims[3] = code.triangular ? 1 : 0;
+    if (row_ptr) memcpy(row_ptr, code.row_ptr.data(), code.row_ptr.size() * 4);
+    if (col_idx) memcpy(col_idx, code.col_idx.data(), code.col_idx.size() * 4);
+    return LDPC_OK;
+}
+
 extern "C" int ldpc_ctx_destroy(ldpc_ctx *ctx)
 {
     free_ctx(ctx);

@@ -62,3 +62,49 @@ def test_product_does_not_import_oracle():
                 txt = open(os.path.join(dirpath, f)).read()
                 for pat in (r"import\s+oracle", r"from\s+oracle", r"oracle/", r"libldpc_oracle", r"orc_"):
                     assert not re.search(pat, txt), f"{f} reaches into the oracle ({pat})"
+
+
+# ---------------------------------------------------------------------------- the C++ MAT-v5 loader, on CPU
+def _scipy_csr(path):
+    from oracle import oracle as orc
+    return orc.Code.from_mat(path)
+
+
+@pytest.mark.parametrize("name", ["n2000_k1000", "n2040_k1530", "n4000_k2000"])
+def test_cpp_loader_reads_exported_codes(name):
+    from ldpc_erasure_codes_b200.codec import read_h_file
+    path = os.path.join(ROOT, "ldpc_erasure_codes_b200", "codes", name + ".mat")
+    m, n, tri, rp, ci = read_h_file(path)
+    ref = _scipy_csr(path)
+    assert (m, n) == (ref.m, ref.n) and tri
+    assert (rp == ref.row_ptr).all() and (ci == ref.col_idx).all()
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/Matlab"), reason="reference not mounted")
+@pytest.mark.parametrize("fname", ["n2000_k1000_no6cycles_triangleForm_OpenCL_H.mat",
+                                   "n2040_k1530_irreg_H_no6cycles_triangleForm.mat",
+                                   "n4000_k2000_no6cycles_triangleForm.mat"])
+def test_cpp_loader_reads_the_reference_files_themselves(fname):
+    """The loader is fed the reference's own committed .mat files (MATLAB-written, different zlib stream)."""
+    from ldpc_erasure_codes_b200.codec import read_h_file
+    path = os.path.join("/root/reference/Matlab", fname)
+    m, n, tri, rp, ci = read_h_file(path)
+    ref = _scipy_csr(path)
+    assert (m, n) == (ref.m, ref.n) and tri
+    assert (rp == ref.row_ptr).all() and (ci == ref.col_idx).all()
+
+
+def test_cpp_loader_rejects_non_sparse_garbage(tmp_path):
+    import scipy.io as sio
+    import numpy as np
+    from ldpc_erasure_codes_b200 import _lib as L
+    p = tmp_path / "x.mat"
+    sio.savemat(str(p), {"other": np.eye(3)})
+    lib = L.load()
+    dims = (C.c_int32 * 4)()
+    assert lib.ldpc_read_h_file(str(p).encode(), C.byref(dims), None, None) == -3      # no H_sparse inside
+    # a full (non-sparse) 0/1 matrix named H_sparse is accepted too
+    H = np.zeros((2, 5)); H[0, [0, 1, 3]] = 1; H[1, [1, 2, 4]] = 1
+    sio.savemat(str(p), {"H_sparse": H})
+    assert lib.ldpc_read_h_file(str(p).encode(), C.byref(dims), None, None) == 0
+    assert list(dims) == [2, 5, 6, 1]
