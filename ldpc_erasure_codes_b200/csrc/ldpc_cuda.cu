@@ -135,6 +135,7 @@ struct ldpc_ctx {
     unsigned long long *d_stats = nullptr;
     unsigned long long *d_phase = nullptr;   // LDPC_CUDA_PHASE_TIMING=1
     uint32_t *d_sim_mask = nullptr;          // ldpc_simulate_fer: masks of one chunk
+    unsigned int *d_work_ctr = nullptr;      // peel kernel's codeword claim counter
     // geometry
     ExecGeom dec, enc;
     int force_W = 0, force_slots = 0;
@@ -220,6 +221,7 @@ static void free_ctx(ldpc_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaFree(c->d_cidx); cudaFree(c->d_vadj); cudaFree(c->d_enc_blob); cudaFree(c->d_sched);
+    cudaFree(c->d_work_ctr);
     cudaFree(c->d_sched_len); cudaFree(c->d_resid); cudaFree(c->d_stats); cudaFree(c->d_fail_scratch); cudaFree(c->d_phase); cudaFree(c->d_sim_mask);
     hybrid_free(c->hyb);
     for (auto &r : c->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
@@ -333,6 +335,7 @@ extern "C" int ldpc_ctx_create(ldpc_ctx **out, const char *h_mat_path, int code_
     CTX_TRY(cudaMalloc(&c->d_fail_scratch, size_t(max_batch)));
     CTX_TRY(cudaMalloc(&c->d_stats, 8 * sizeof(unsigned long long)));
     CTX_TRY(cudaMemset(c->d_stats, 0, 8 * sizeof(unsigned long long)));
+    CTX_TRY(cudaMalloc(&c->d_work_ctr, sizeof(unsigned int)));
     if (const char *e = getenv("LDPC_CUDA_PHASE_TIMING")) {
         if (*e && *e != '0') {
             CTX_TRY(cudaMalloc(&c->d_phase, 8 * sizeof(unsigned long long)));
@@ -565,11 +568,17 @@ extern "C" int ldpc_fill_random(void *d_dst, int64_t nbytes, uint32_t seed, uint
 // ------------------------------------------------------------------------------------------
 // decoder
 // ------------------------------------------------------------------------------------------
+// One peel -> executor (-> elimination) pass over B <= max_batch codewords.  (Cutting a batch into pieces
+// on two internal streams so that one piece's executor overlaps the next one's schedule compiler was
+// measured and is no faster: both kernels fill an SM's shared memory and cannot share one.)
 static int decode_chunk(ldpc_ctx *c, const uint8_t *d_cw, const uint32_t *d_mask, uint8_t *d_out, uint8_t *d_fail,
                         int max_iter, int mode, long long B, cudaStream_t st)
 {
+    uint8_t *const sched = c->d_sched;
+    uint32_t *const sched_len = c->d_sched_len;
     PeelParams pp;
-    pp.mask = d_mask; pp.sched = c->d_sched; pp.sched_len = c->d_sched_len;
+    pp.mask = d_mask; pp.sched = sched; pp.sched_len = sched_len;
+    pp.work_ctr = c->d_work_ctr;
     pp.fail = d_fail ? d_fail : c->d_fail_scratch; pp.resid = c->d_resid; pp.stats = c->d_stats;
     pp.cidx = c->d_cidx; pp.vadj = c->d_vadj; pp.B = B; pp.n = c->code.n; pp.k = c->code.k; pp.m = c->code.m;
     pp.RW = c->code.RW; pp.VW = c->code.VW; pp.NW = c->NW; pp.MW = c->MW; pp.stride = c->sched_stride;
@@ -583,6 +592,7 @@ static int decode_chunk(ldpc_ctx *c, const uint8_t *d_cw, const uint32_t *d_mask
         pp.ge_list = c->hyb.d_list; pp.ge_count = c->hyb.d_count;
     }
     const int grid = int(std::min<long long>(c->num_sms, (B + c->peel_groups - 1) / c->peel_groups));
+    CUDA_TRY(cudaMemsetAsync(pp.work_ctr, 0, sizeof(unsigned int), st));
     {
         ProfScope ps(c, LDPC_K_PEEL, st);
         pick_peel(c->MW, c->code.VW)<<<grid, c->peel_groups * c->peel_G, c->peel_smem, st>>>(pp);
@@ -591,13 +601,13 @@ static int decode_chunk(ldpc_ctx *c, const uint8_t *d_cw, const uint32_t *d_mask
     { int rcd = debug_sync("peel_schedule_kernel", st); if (rcd) return rcd; }
     const bool pattern_only = d_cw == nullptr;   // error-rate run: no payload
     if (!pattern_only) {
-        int rc = launch_exec(c, c->dec, d_cw, c->code.n, d_out, c->code.k, c->d_sched, c->d_sched_len, c->sched_stride, B, st,
+        int rc = launch_exec(c, c->dec, d_cw, c->code.n, d_out, c->code.k, sched, sched_len, c->sched_stride, B, st,
                              mode == LDPC_MODE_HYBRID ? c->hyb.d_full : nullptr);
         if (rc) return rc;
     }
     if (mode == LDPC_MODE_HYBRID) {
         GeParams gp;
-        gp.mask = d_mask; gp.sched = c->d_sched; gp.list = c->hyb.d_list; gp.list_count = c->hyb.d_count;
+        gp.mask = d_mask; gp.sched = sched; gp.list = c->hyb.d_list; gp.list_count = c->hyb.d_count;
         gp.full = pattern_only ? nullptr : c->hyb.d_full; gp.out = d_out; gp.fail = pp.fail; gp.stats = c->d_stats; gp.cidx = c->d_cidx;
         gp.gmat = c->hyb.d_gmat; gp.n = c->code.n; gp.k = c->code.k; gp.m = c->code.m; gp.RW = c->code.RW; gp.NW = c->NW;
         gp.MW = c->MW; gp.S = c->S; gp.stride = c->sched_stride; gp.RSW = c->hyb.RSW;
@@ -622,10 +632,12 @@ extern "C" int ldpc_decode(ldpc_ctx *c, const void *d_cw, const uint32_t *d_mask
     if (max_iter < 0 || max_iter > 1000000) return fail(LDPC_ERR_ARG, "max_iter out of range");
     CUDA_TRY(cudaSetDevice(c->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const uint8_t *cw = static_cast<const uint8_t *>(d_cw);
+    uint8_t *out = static_cast<uint8_t *>(d_out);
+    const size_t in_cw = size_t(c->code.n) * c->S, out_cw = size_t(c->code.k) * c->S;
     for (long long b0 = 0; b0 < B; b0 += c->max_batch) {
         const long long nb = std::min<long long>(c->max_batch, B - b0);
-        int rc = decode_chunk(c, static_cast<const uint8_t *>(d_cw) + size_t(b0) * c->code.n * c->S,
-                              d_mask + size_t(b0) * c->NW, static_cast<uint8_t *>(d_out) + size_t(b0) * c->code.k * c->S,
+        int rc = decode_chunk(c, cw + size_t(b0) * in_cw, d_mask + size_t(b0) * c->NW, out + size_t(b0) * out_cw,
                               d_fail ? d_fail + b0 : nullptr, max_iter, mode, nb, st);
         if (rc) return rc;
     }

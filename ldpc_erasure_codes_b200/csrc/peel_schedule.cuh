@@ -33,6 +33,7 @@ namespace ldpc {
 
 struct PeelParams {
     const uint32_t *mask;       // [B][NW]
+    unsigned int *work_ctr;     // zeroed before the launch: next unclaimed codeword
     uint8_t *sched;             // [B][stride] schedule blobs
     uint32_t *sched_len;        // [B] bytes of each blob (multiple of 16)
     uint8_t *fail;              // [B] or nullptr
@@ -133,9 +134,16 @@ __global__ void __launch_bounds__(1024) peel_schedule_kernel(const PeelParams p)
     const int dummy_off = msk_off + NW + 1 + lane % 3;     // (distinct lanes may share a scratch word: values are never read back)   // scratch words behind the mask 
 
     unsigned int my_fail = 0, my_rs = 0, my_frames = 0;
-    const long long stride = (long long)gridDim.x * p.groups_per_block;
+    // Codewords are claimed a warp-load (32/G) at a time from a global counter: replay lengths vary by
+    // codeword, and a static split leaves most of the GPU idle in the last round.
+    auto claim = [&]() -> long long {
+        unsigned int base = 0;
+        if (wl == 0) base = atomicAdd(p.work_ctr, (unsigned int)(32 / G));
+        base = __shfl_sync(FULL, base, 0);
+        return (long long)base + wl / G;
+    };
 
-    for (long long cw = (long long)blockIdx.x * p.groups_per_block + grp; __any_sync(FULL, cw < p.B); cw += stride) {
+    for (long long cw = claim(); __any_sync(FULL, cw < p.B); cw = claim()) {
         const bool valid = cw < p.B;
         // ---- 1. erasure mask -> shared, erasure counts ---------------------------------
         int n_er = 0, rem_sys = 0;
