@@ -55,6 +55,9 @@ static int allow_max_smem(const void *func, int smem_optin)
     return LDPC_OK;
 }
 
+// LDPC_CUDA_GE_CTA_ONLY=1: elimination stage uses the CTA-per-codeword kernel only (tests compare both paths)
+static bool ge_cta_only() { const char *e = getenv("LDPC_CUDA_GE_CTA_ONLY"); return e && *e && *e != '0'; }
+
 // LDPC_CUDA_DEBUG_SYNC=1: synchronise after every launch so that a faulting kernel is named
 static int debug_sync(const char *what, cudaStream_t st)
 {
@@ -588,7 +591,7 @@ static int decode_chunk(ldpc_ctx *c, const uint8_t *d_cw, const uint32_t *d_mask
     if (mode == LDPC_MODE_HYBRID) {
         int rch = hybrid_prepare(c->hyb, c->code, c->S, c->NW, c->MW, c->num_sms, c->smem_optin, c->max_batch, g_err);
         if (rch) return rch;
-        CUDA_TRY(cudaMemsetAsync(c->hyb.d_count, 0, 4, st));
+        CUDA_TRY(cudaMemsetAsync(c->hyb.d_count, 0, 8 * 4, st));
         pp.ge_list = c->hyb.d_list; pp.ge_count = c->hyb.d_count;
     }
     const int grid = int(std::min<long long>(c->num_sms, (B + c->peel_groups - 1) / c->peel_groups));
@@ -611,6 +614,20 @@ static int decode_chunk(ldpc_ctx *c, const uint8_t *d_cw, const uint32_t *d_mask
         gp.full = pattern_only ? nullptr : c->hyb.d_full; gp.out = d_out; gp.fail = pp.fail; gp.stats = c->d_stats; gp.cidx = c->d_cidx;
         gp.gmat = c->hyb.d_gmat; gp.n = c->code.n; gp.k = c->code.k; gp.m = c->code.m; gp.RW = c->code.RW; gp.NW = c->NW;
         gp.MW = c->MW; gp.S = c->S; gp.stride = c->sched_stride; gp.RSW = c->hyb.RSW;
+        // warp-per-codeword stages first; what does not fit their shared-memory slots falls through
+        const unsigned int *lists[3] = {c->hyb.d_list, c->hyb.d_list2, c->hyb.d_list3};
+        int li = 0;
+        for (int sg = 0; sg < 2 && c->hyb.wpc[sg] > 0 && !ge_cta_only(); sg++) {
+            if (sg == 1 && c->hyb.wpc[1] == c->hyb.wpc[0]) break;    // same slots: nothing more would fit
+            GeWarpParams wp;
+            wp.g = gp; wp.g.list = lists[li]; wp.g.list_count = c->hyb.d_count + li;
+            wp.list_out = const_cast<unsigned int *>(lists[li + 1]); wp.count_out = c->hyb.d_count + li + 1;
+            wp.work_ctr = c->hyb.d_count + 3 + sg; wp.slot_words = c->hyb.slot_words[sg];
+            ProfScope ps(c, LDPC_K_HYBRID, st);
+            hybrid_ge_warp_kernel<<<c->num_sms, 32 * c->hyb.wpc[sg], size_t(c->hyb.wpc[sg]) * c->hyb.slot_words[sg] * 4, st>>>(wp);
+            li++;
+        }
+        gp.list = lists[li]; gp.list_count = c->hyb.d_count + li;
         {
             ProfScope ps(c, LDPC_K_HYBRID, st);
             if (gp.gmat) hybrid_ge_kernel<true><<<c->hyb.grid, kGeThreads, c->hyb.smem, st>>>(gp);

@@ -312,6 +312,28 @@ def test_hybrid_n4000_bursty_stress(codecs):
     assert (ref["status"] > 0).any()
 
 
+def test_hybrid_warp_and_cta_kernels_agree(codecs, monkeypatch):
+    """The warp-per-codeword stages and the CTA-per-codeword kernel are two solvers of the same system."""
+    codec = codecs(1, 64)
+    code, cw, rx, mask, flags = _scenario(codec, 1, 300, 13, 4711, 64)
+    ref = _hybrid_check(codec, code, rx, mask, flags)
+    assert (ref["status"] == 1).sum() > 40
+    monkeypatch.setenv("LDPC_CUDA_GE_CTA_ONLY", "1")
+    _hybrid_check(codec, code, rx, mask, flags)
+
+
+@pytest.mark.parametrize("wpc", ["16", "7"])
+def test_hybrid_fall_through_when_slots_are_small(monkeypatch, wpc):
+    """Small shared-memory slots: stage 1 defers what does not fit to stage 2 / the CTA kernel; same answers."""
+    from ldpc_erasure_codes_b200.codec import LdpcCodec
+    monkeypatch.setenv("LDPC_CUDA_GE_WPC", wpc)
+    codec = LdpcCodec(code=1, symbol_bytes=32, device=0, max_batch=256)
+    code, cw, rx, mask, flags = _scenario(codec, 1, 200, 13, 99, 32)
+    ref = _hybrid_check(codec, code, rx, mask, flags)
+    assert (ref["status"] == 1).sum() > 20
+    codec.close()
+
+
 # ------------------------------------------------------------------------------- Reed-Solomon GF(256)
 @pytest.fixture(scope="module")
 def rs_codecs():

@@ -4,20 +4,25 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from ldpc_erasure_codes_b200.codec import LdpcCodec, fill_random
-B = int(os.environ.get("B", "65536")); P = int(os.environ.get("P", "13")); S = int(os.environ.get("S", "64")); R = int(os.environ.get("R", "10"))
+B = int(os.environ.get("B", "65536")); P = int(os.environ.get("P", "13")); S = int(os.environ.get("S", "64")); R = int(os.environ.get("R", "10")); MODE = os.environ.get("MODE", "peel"); IT = int(os.environ.get("IT", "50" if MODE == "peel" else "10"))
 codec = LdpcCodec(code=int(os.environ.get("CODE", "1")), symbol_bytes=S, device=0, max_batch=B)
 info = torch.empty((B, codec.k, S), dtype=torch.uint8, device="cuda"); fill_random(info, 1)
 cw = codec.encode(info); mask = codec.gen_erasures(B, 4242, P=P, payload=cw)
 out = torch.empty_like(info); fail = torch.empty(B, dtype=torch.uint8, device="cuda")
-for _ in range(3): codec.decode(cw, mask, out=out, fail=fail)
+for _ in range(3): codec.decode(cw, mask, max_iter=IT, mode=MODE, out=out, fail=fail)
 ts = []
 for _ in range(R):
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize(); e0.record(); codec.decode(cw, mask, out=out, fail=fail); e1.record(); torch.cuda.synchronize()
+    torch.cuda.synchronize(); e0.record(); codec.decode(cw, mask, max_iter=IT, mode=MODE, out=out, fail=fail); e1.record(); torch.cuda.synchronize()
     ts.append(e0.elapsed_time(e1))
 ts.sort()
 ok = fail == 0
 assert bool((out[ok] == info[ok]).all()), "mismatch"
-codec.profile_enable(True); codec.decode(cw, mask, out=out, fail=fail); pr = codec.profile_read(reset=True)
-print(f"B={B} P={P} split_min={os.environ.get('LDPC_CUDA_SPLIT_MIN','default')} pieces={os.environ.get('LDPC_CUDA_SPLIT_PIECES','default')}: "
+codec.profile_enable(True); codec.decode(cw, mask, max_iter=IT, mode=MODE, out=out, fail=fail); pr = codec.profile_read(reset=True)
+hy = pr.get("hybrid", {}).get("ms", 0.0)
+print(f"B={B} P={P} mode={MODE} hybrid_ms={hy:.3f}: "
       f"{ts[len(ts)//2]:.3f} ms/call (min {ts[0]:.3f}); serial peel {pr['peel']['ms']:.3f} exec {pr['exec_decode']['ms']:.3f}  FER {float(fail.float().mean()):.4f}")
+if MODE == "hybrid":   # the same frames, pattern only (no payload): isolates the elimination from the syndrome gathers
+    codec.profile_read(reset=True); codec.profile_enable(True)
+    codec.simulate_fer(B, 4242, P=P, max_iter=IT, mode="hybrid"); pr = codec.profile_read(reset=True)
+    print(f"  pattern-only: hybrid_ms={pr['hybrid']['ms']:.3f} peel {pr['peel']['ms']:.3f}")
