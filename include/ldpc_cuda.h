@@ -173,8 +173,12 @@ int ldpc_reset_stats(ldpc_ctx *ctx);
  * when enabled, every kernel the context launches is bracketed by CUDA events on the
  * launching stream; ldpc_profile_read() synchronises and returns per-kernel device time.
  * Launch counters are always maintained.                                                 */
-enum { LDPC_K_PEEL = 0, LDPC_K_EXEC_DECODE = 1, LDPC_K_EXEC_ENCODE = 2, LDPC_K_HYBRID = 3,
-       LDPC_K_CHANNEL = 4, LDPC_K_KINDS = 8 };
+enum { LDPC_K_PEEL = 0, LDPC_K_EXEC_DECODE = 1, LDPC_K_EXEC_ENCODE = 2,
+       LDPC_K_HYBRID = 3,        /* elimination stage 1: inactivation decoding, one warp per codeword       */
+       LDPC_K_CHANNEL = 4,
+       LDPC_K_HYBRID_WARP = 5,   /* stage 2: per-warp Gauss-Jordan on what stage 1 deferred (rare)          */
+       LDPC_K_HYBRID_CTA = 6,    /* stage 3: CTA-per-codeword Gauss-Jordan on what stage 2 deferred         */
+       LDPC_K_KINDS = 8 };
 typedef struct ldpc_profile {
     double ms[LDPC_K_KINDS];        /* summed device time per kernel kind (profiling on)  */
     int64_t launches[LDPC_K_KINDS]; /* kernel launches per kind since create / last reset */
@@ -182,6 +186,8 @@ typedef struct ldpc_profile {
      * environment: SM cycles the executor's group leaders spent per phase, summed over units:
      * [0] claim + TMA issue, [1] waiting for the load, [2] XOR, [3] store, [4] number of units   */
     uint64_t exec_phase_cycles[8];
+    uint64_t ge_phase_cycles[8];    /* LDPC_CUDA_PHASE_TIMING=1: inactivation stage, warp cycles per phase: setup, rows,
+                                       adjacency+syndromes, peel/inactivate, dense solve, output; [6] = codewords      */
 } ldpc_profile;
 int ldpc_profile_enable(ldpc_ctx *ctx, int on);
 int ldpc_profile_read(ldpc_ctx *ctx, ldpc_profile *out, int reset);

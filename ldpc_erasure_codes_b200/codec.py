@@ -168,6 +168,7 @@ class LdpcCodec:
         _lib.check(self.lib.ldpc_profile_read(self._h, C.byref(p), 1 if reset else 0))
         d = {name: dict(ms=p.ms[i], launches=p.launches[i]) for i, name in enumerate(_lib.KIND_NAMES)}
         d["exec_phase_cycles"] = list(p.exec_phase_cycles)
+        d["ge_phase_cycles"] = list(p.ge_phase_cycles)
         return d
 
 

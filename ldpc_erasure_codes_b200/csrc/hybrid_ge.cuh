@@ -42,6 +42,9 @@ struct GeParams {
     uint8_t *fail;                   // [B]
     unsigned long long *stats;       // [3] ml_attempts, [4] ml_failures, [5] ml_recovered
     const uint16_t *cidx;            // [m][RW]
+    const uint16_t *vadj;            // [n][VW] variable -> checks
+    unsigned long long *phase_cycles;   // optional [8]: inactivation stage phase timers
+    int VW;
     uint32_t *gmat;                  // per-CTA global workspace for [A | I], or nullptr (shared memory)
     int n, k, m, RW, NW, MW, S, stride;
     int RSW;                         // words per matrix row: 2 * MW + 1 (odd: rows start in different banks)
@@ -460,13 +463,377 @@ __global__ void __launch_bounds__(512) hybrid_ge_warp_kernel(const GeWarpParams 
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// First stage: inactivation decoding, one warp per stalled codeword.
+//
+// A stopping set is sparse: it stalls peeling only because no check has exactly ONE unknown left.
+// Declaring a few unknowns "inactive" (to be solved later) restarts peeling; on n2040/k1530 at 13/64
+// about 6 inactivations let peeling finish the other ~250 unknowns.  This is Gauss-Jordan elimination
+// with a good pivot order, so its verdict (full column rank or not) and its solution are those of the
+// reference's elimination -- but a peeled pivot touches only the <= VW-1 other checks of its variable
+// instead of ~35 filled-in rows, and the dense part is |inactive| x |inactive|.
+//
+//   per involved check (row): state = [used:1 | deg:15 | xor of its ACTIVE unknowns:16], ipart = which
+//   inactive unknowns its equation contains (<= 64), b = 64 bytes of right-hand side.
+//   phase 1  while unknowns are active: pop a row with deg 1 -> its unknown u is "peeled" with this row as
+//            pivot; every other check of u (static adjacency, H's column) gets  row ^= pivot row  (ipart, b)
+//            and deg-1.  No such row: take the unused row of smallest degree and inactivate one of its
+//            unknowns (bit q of ipart in all its checks, deg-1).
+//   phase 2  the unused rows are now equations in the inactive unknowns only: Gauss-Jordan on
+//            [ipart | b] (<= 64 columns); no pivot => rank deficient => ml_fail.
+//   phase 3  unknown of pivot row r  =  b[r] ^ XOR of the inactive unknowns in ipart[r]; systematic
+//            ones are written to the decoder output.  (All of phase 3 is independent work.)
+// More than 64 inactivations, or rows that do not fit the slot: deferred to the next stage.
+// ------------------------------------------------------------------------------------------
+constexpr int kInactMax = 64;
+
+__host__ __device__ inline int ge_inact_fixed_words(int m, int NW, int MW)
+{   // er[NW+1] pref[NW+1] d1[MW] act[MW] icol/ipiv[64] | u16: inv_rowmap rowmap pl_col pl_row varlist, [m] each
+    return ((2 * (NW + 1) + 2 * MW + kInactMax) + 5 * ((m + 1) / 2) + 3) & ~3;
+}
+__host__ __device__ inline long long ge_inact_area_words(int rows, int e, int VW, bool payload)
+{   // state[R] | ipart[R] u64 | nbr[e][VW] u16 | b[R][16]
+    return ((3ll * rows + 3) & ~3ll) + ((((long long)e * VW + 1) / 2 + 3) & ~3ll) + (payload ? 16ll * rows : 0);
+}
+
+__global__ void __launch_bounds__(512) hybrid_inact_kernel(const GeWarpParams q)
+{
+    extern __shared__ __align__(16) uint32_t gw_smem[];
+    constexpr unsigned FULL = 0xFFFFFFFFu;
+    constexpr uint32_t USED = 0x80000000u, TAKEN = 0x40000000u;
+    const GeParams &p = q.g;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int m = p.m, NW = p.NW, MW = p.MW, RW = p.RW, VW = p.VW;
+    uint32_t *er = gw_smem + size_t(warp) * q.slot_words;     // residual erased set (the unknowns)
+    uint32_t *pref = er + NW + 1;                               // column number of the first unknown of each mask word
+    uint32_t *d1 = pref + NW + 1;                               // rows whose degree became 1
+    uint32_t *act = d1 + MW;                                    // columns still active
+    uint16_t *icol = reinterpret_cast<uint16_t *>(act + MW);    // [64] inactive columns, [64] their pivot rows
+    uint16_t *ipiv = icol + kInactMax;
+    const int mp = m + (m & 1);
+    uint16_t *inv_rowmap = ipiv + kInactMax;
+    uint16_t *rowmap = inv_rowmap + mp;
+    uint16_t *pl_col = rowmap + mp;
+    uint16_t *pl_row = pl_col + mp;
+    uint16_t *varlist = pl_row + mp;
+    uint32_t *area = er + ge_inact_fixed_words(m, NW, MW);
+    const long long area_words = q.slot_words - ge_inact_fixed_words(m, NW, MW);
+    const bool payload = p.full != nullptr;
+    const unsigned int count = *p.list_count;
+    const int qd = lane & 3, hs = lane >> 2;                    // payload lanes: 16-byte quarter, hit slot
+
+    for (;;) {
+        unsigned int li = 0;
+        if (lane == 0) li = atomicAdd(q.work_ctr, 1u);
+        li = __shfl_sync(FULL, li, 0);
+        if (li >= count) break;
+        const long long cw = p.list[li];
+        const uint32_t *hdr = reinterpret_cast<const uint32_t *>(p.sched + cw * (long long)p.stride);
+        const int ne = int(hdr[0]);
+        bool ok = true, defer = false;
+        long long tmark = p.phase_cycles ? clock64() : 0;
+        auto lap = [&](int ph) {
+            if (p.phase_cycles) {
+                const long long t = clock64();
+                if (lane == 0) atomicAdd(&p.phase_cycles[ph], (unsigned long long)(t - tmark));
+                tmark = t;
+            }
+        };
+        const int nchunk = payload ? (p.S + 63) / 64 : 1;
+        for (int chn = 0; ok && !defer && chn < nchunk; chn++) {
+            const int ch = chn * 64;
+            const int cb = payload ? min(64, p.S - ch) : 0;
+            // ---- residual erased set, column numbering -----------------------------------------------
+            for (int w = lane; w < NW; w += 32) {
+                uint32_t x = p.mask[cw * NW + w];
+                if (w == NW - 1 && (p.n & 31)) x &= FULL >> (32 - (p.n & 31));
+                er[w] = x;
+            }
+            for (int w = lane; w < MW; w += 32) d1[w] = 0u;
+            __syncwarp();
+            for (int i = lane; i < ne; i += 32) {
+                const uint32_t v = hdr[4 + i] & 0xFFFFu;
+                atomicAnd(&er[v >> 5], ~(1u << (v & 31)));
+            }
+            __syncwarp();
+            int e = 0;
+            for (int w0 = 0; w0 < NW; w0 += 32) {
+                const int w = w0 + lane;
+                const int c = w < NW ? __popc(er[w]) : 0;
+                int inc = c;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(FULL, inc, o);
+                    if (lane >= o) inc += t;
+                }
+                if (w < NW) pref[w] = uint32_t(e + inc - c);
+                e += __shfl_sync(FULL, inc, 31);
+            }
+            __syncwarp();
+            if (e > m) { ok = false; break; }                    // more unknowns than checks: no full column rank
+            for (int w = lane; w < NW; w += 32) {
+                uint32_t x = er[w];
+                uint32_t b = pref[w];
+                while (x) { varlist[b++] = uint16_t(w * 32 + __ffs(x) - 1); x &= x - 1u; }
+            }
+            lap(0);
+            for (int w = lane; w < MW; w += 32) act[w] = (w * 32 + 32 <= e) ? FULL : (w * 32 < e ? (FULL >> (32 - (e - w * 32))) : 0u);
+            // ---- rows: the checks with a residual member; state = [deg | xor of the active columns] ------
+            int R = 0;
+            for (int r0 = 0; r0 < m; r0 += 32) {
+                const int r = r0 + lane;
+                uint32_t cnt = 0, xr = 0;
+                if (r < m)
+                    for (int j0 = 0; j0 < RW; j0 += 8) {
+                        const uint4 r4 = __ldg(reinterpret_cast<const uint4 *>(p.cidx + r * RW + j0));
+                        const uint32_t rr[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+                        for (int t = 0; t < 8; t++) {
+                            const uint32_t u = (t & 1) ? (rr[t >> 1] >> 16) : (rr[t >> 1] & 0xFFFFu);
+                            const uint32_t us = u == 0xFFFFu ? 0u : u;
+                            const uint32_t x = er[us >> 5];
+                            const uint32_t bit = u == 0xFFFFu ? 0u : (x >> (us & 31)) & 1u;
+                            const uint32_t col = pref[us >> 5] + __popc(x & ((1u << (us & 31)) - 1u));
+                            cnt += bit;
+                            xr ^= (0u - bit) & col;
+                        }
+                    }
+                const unsigned bal = __ballot_sync(FULL, cnt > 0);
+                const int ri = R + __popc(bal & ((1u << lane) - 1u));
+                if (r < m) inv_rowmap[r] = cnt > 0 ? uint16_t(ri) : uint16_t(0xFFFFu);
+                if (cnt > 0) rowmap[ri] = uint16_t(r);
+                R += __popc(bal);
+                if (cnt > 0 && ri < area_words) area[ri] = (cnt << 16) | xr;     // state (the fit is checked below)
+            }
+            __syncwarp();
+            lap(1);
+            if (ge_inact_area_words(R, e, VW, payload) > area_words) { defer = true; break; }
+            uint32_t *state = area;                                              // [R]
+            unsigned long long *ipart = reinterpret_cast<unsigned long long *>(area + ((R + 1) & ~1));   // [R]
+            uint16_t *nbr = reinterpret_cast<uint16_t *>(area + ((3 * R + 3) & ~3));   // [e][VW] rows of each unknown
+            uint32_t *bmat = area + ((3 * R + 3) & ~3) + (((e * VW + 1) / 2 + 3) & ~3);   // [R][16], 16-byte aligned
+            for (int ri = lane; ri < R; ri += 32) {
+                ipart[ri] = 0ull;
+                if ((state[ri] >> 16) == 1u) atomicOr(&d1[ri >> 5], 1u << (ri & 31));
+            }
+            for (int i = lane; i < e * VW; i += 32) {            // H's columns for the unknowns, as compact row numbers
+                const uint32_t chk = __ldg(p.vadj + size_t(varlist[i / VW]) * VW + (i % VW));
+                nbr[i] = chk == 0xFFFFu ? uint16_t(0xFFFFu) : inv_rowmap[chk];
+            }
+            if (payload) {   // syndromes: XOR of the KNOWN members, 8 rows x 4 quarters per pass, 16 gathers in flight
+                const uint8_t *full = p.full + size_t(cw) * p.n * p.S + ch;
+                for (int ri = hs; ri < R; ri += 8) {
+                    uint4 acc = make_uint4(0u, 0u, 0u, 0u);
+                    if (qd * 16 < cb) {
+                        const int r = rowmap[ri];
+                        for (int j0 = 0; j0 < RW; j0 += 16) {
+                            uint4 v[16];
+                            bool use[16];
+#pragma unroll
+                            for (int h = 0; h < 2; h++) {
+                                const bool in = j0 + 8 * h < RW;      // RW is a multiple of 8
+                                const uint4 r4 = in ? __ldg(reinterpret_cast<const uint4 *>(p.cidx + r * RW + j0 + 8 * h))
+                                                    : make_uint4(FULL, FULL, FULL, FULL);
+                                const uint32_t rr[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+                                for (int t = 0; t < 8; t++) {
+                                    const uint32_t u = (t & 1) ? (rr[t >> 1] >> 16) : (rr[t >> 1] & 0xFFFFu);
+                                    const uint32_t us = u == 0xFFFFu ? 0u : u;
+                                    use[8 * h + t] = u != 0xFFFFu && !((er[us >> 5] >> (us & 31)) & 1u);
+                                    v[8 * h + t] = *reinterpret_cast<const uint4 *>(full + size_t(use[8 * h + t] ? u : 0u) * p.S + qd * 16);
+                                }
+                            }
+#pragma unroll
+                            for (int t = 0; t < 16; t++)
+                                if (use[t]) { acc.x ^= v[t].x; acc.y ^= v[t].y; acc.z ^= v[t].z; acc.w ^= v[t].w; }
+                        }
+                    }
+                    *reinterpret_cast<uint4 *>(bmat + size_t(ri) * 16 + qd * 4) = acc;
+                }
+            }
+            __syncwarp();
+
+            lap(2);
+            // ---- phase 1: peel, inactivating when stuck --------------------------------------------------
+            const int MWc = (R + 31) >> 5;
+            const int RPL = (R + 31) >> 5;
+            int remaining = e, npeel = 0, ninact = 0;
+            while (remaining > 0) {
+                int ri = -1;                                     // lowest row marked degree-1
+                for (int w0 = 0; w0 < MWc && ri < 0; w0 += 32) {
+                    const uint32_t x = (w0 + lane < MWc) ? d1[w0 + lane] : 0u;
+                    const unsigned bal = __ballot_sync(FULL, x != 0u);
+                    if (bal) {
+                        const int fl = __ffs(bal) - 1;
+                        const uint32_t xf = __shfl_sync(FULL, x, fl);
+                        ri = (w0 + fl) * 32 + __ffs(xf) - 1;
+                        if (lane == fl) d1[w0 + fl] = x & (x - 1u);
+                    }
+                }
+                uint32_t col;
+                const bool peel = ri >= 0;
+                if (peel) {
+                    const uint32_t st = state[ri];
+                    if ((st >> 16) != 1u) { __syncwarp(); continue; }     // stale mark (degree dropped to 0)
+                    col = st & 0xFFFFu;
+                } else {
+                    // stuck: unused row of smallest degree >= 2; inactivate its first active unknown
+                    unsigned best = 0xFFFFFFFFu;
+                    for (int i0 = 0; i0 < RPL; i0 += 8) {
+                        uint32_t sv[8];
+#pragma unroll
+                        for (int t = 0; t < 8; t++) sv[t] = state[min(lane + 32 * (i0 + t), R - 1)];
+#pragma unroll
+                        for (int t = 0; t < 8; t++) {
+                            const int rr_ = lane + 32 * (i0 + t);
+                            const uint32_t dg = sv[t] >> 16;          // (used rows carry the flag in this field)
+                            if (rr_ < R && dg >= 2u && dg < 0x4000u) best = min(best, (dg << 16) | uint32_t(rr_));
+                        }
+                    }
+                    best = __reduce_min_sync(FULL, best);
+                    if (best == 0xFFFFFFFFu) { ok = false; break; }       // an unknown that no equation constrains
+                    if (ninact == kInactMax) { defer = true; break; }
+                    ri = int(best & 0xFFFFu);
+                    const int r = rowmap[ri];
+                    uint32_t mc = 0xFFFFu;
+                    bool a = false;
+                    if (lane < RW) {
+                        const uint32_t mu = __ldg(p.cidx + r * RW + lane);
+                        if (mu != 0xFFFFu) {
+                            const uint32_t x = er[mu >> 5];
+                            if ((x >> (mu & 31)) & 1u) {
+                                mc = pref[mu >> 5] + __popc(x & ((1u << (mu & 31)) - 1u));
+                                a = (act[mc >> 5] >> (mc & 31)) & 1u;
+                            }
+                        }
+                    }
+                    const unsigned bal = __ballot_sync(FULL, a);          // (!= 0: the row's degree counts active members)
+                    col = __shfl_sync(FULL, mc, __ffs(bal) - 1);
+                }
+                // the rows of this unknown (static: H's column)
+                uint32_t rj = 0xFFFFu;
+                if (lane < VW) rj = nbr[col * VW + lane];
+                const bool nb = rj != 0xFFFFu;
+                const bool other = nb && !(peel && int(rj) == ri);
+                const unsigned long long pI = peel ? ipart[ri] : (1ull << ninact);
+                uint4 pb = make_uint4(0u, 0u, 0u, 0u);
+                if (payload && peel) pb = *reinterpret_cast<const uint4 *>(bmat + size_t(ri) * 16 + qd * 4);
+                if (other) {
+                    const uint32_t s2 = state[rj];
+                    const uint32_t n2 = (((s2 >> 16) - 1u) << 16) | ((s2 & 0xFFFFu) ^ col);
+                    state[rj] = n2;
+                    ipart[rj] ^= pI;                                     // (inactivation: a new bit, so ^ sets it)
+                    if ((n2 >> 16) == 1u) atomicOr(&d1[rj >> 5], 1u << (rj & 31));
+                }
+                if (peel && nb && int(rj) == ri) state[ri] = USED;
+                if (lane == 0) {
+                    act[col >> 5] &= ~(1u << (col & 31));
+                    if (peel) { pl_col[npeel] = uint16_t(col); pl_row[npeel] = uint16_t(ri); }
+                    else icol[ninact] = uint16_t(col);
+                }
+                if (payload && peel) {                                   // b[row] ^= b[pivot], eight rows per instruction
+                    const unsigned hb = __ballot_sync(FULL, other);
+                    const int nh = __popc(hb);
+                    for (int h0 = 0; h0 < nh; h0 += 8) {
+                        const int src = __fns(hb, 0, h0 + hs + 1);       // lane holding the (h0+hs)-th hit, -1 if none
+                        const int r2 = __shfl_sync(FULL, int(rj), src < 0 ? 0 : src);
+                        if (src >= 0 && src < 32) {
+                            uint4 *br = reinterpret_cast<uint4 *>(bmat + size_t(r2) * 16 + qd * 4);
+                            uint4 a4 = *br;
+                            a4.x ^= pb.x; a4.y ^= pb.y; a4.z ^= pb.z; a4.w ^= pb.w;
+                            *br = a4;
+                        }
+                    }
+                }
+                if (peel) npeel++; else ninact++;
+                remaining--;
+                __syncwarp();
+            }
+            lap(3);
+            if (!ok || defer) break;
+
+            // ---- phase 2: the unused rows are equations in the inactive unknowns only ----------------------
+            for (int c = 0; c < ninact; c++) {
+                unsigned best = 0xFFFFFFFFu;
+                for (int r0 = lane; r0 < R; r0 += 32)
+                    if (!(state[r0] & (USED | TAKEN)) && ((ipart[r0] >> c) & 1u)) { best = uint32_t(r0); break; }
+                best = __reduce_min_sync(FULL, best);
+                if (best == 0xFFFFFFFFu) { ok = false; break; }           // no pivot: rank deficient (HybridML.m:59-62)
+                const int pr = int(best);
+                const unsigned long long pI = ipart[pr];
+                uint32_t pb = 0u;
+                if (payload && lane < 16) pb = bmat[size_t(pr) * 16 + lane];
+                __syncwarp();
+                if (lane == 0) { state[pr] |= TAKEN; ipiv[c] = uint16_t(pr); }
+                for (int r0 = 0; r0 < R; r0 += 32) {
+                    const int r2 = r0 + lane;
+                    const bool hit = r2 < R && r2 != pr && !(state[r2] & USED) && ((ipart[r2] >> c) & 1u);
+                    if (hit) ipart[r2] ^= pI;
+                    if (payload) {
+                        unsigned hb = __ballot_sync(FULL, hit);
+                        while (hb) {
+                            const int hl = __ffs(hb) - 1;
+                            hb &= hb - 1u;
+                            if (lane < 16) bmat[size_t(r0 + hl) * 16 + lane] ^= pb;
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+            lap(4);
+            if (!ok) break;
+
+            // ---- phase 3: read the unknowns off their pivot rows ----------------------------------------------
+            if (payload) {
+                uint8_t *out = p.out + size_t(cw) * p.k * p.S + ch;
+                for (int i = hs; i < npeel + ninact; i += 8) {
+                    const bool pe = i < npeel;
+                    const int u = varlist[pe ? pl_col[i] : icol[i - npeel]];
+                    const int r = pe ? pl_row[i] : ipiv[i - npeel];
+                    if (u >= p.k || qd * 16 >= cb) continue;              // only systematic symbols are output
+                    uint4 acc = *reinterpret_cast<const uint4 *>(bmat + size_t(r) * 16 + qd * 4);
+                    unsigned long long bits = pe ? ipart[r] : 0ull;
+                    while (bits) {
+                        const int c = __ffsll((long long)bits) - 1;
+                        bits &= bits - 1ull;
+                        const uint4 v = *reinterpret_cast<const uint4 *>(bmat + size_t(ipiv[c]) * 16 + qd * 4);
+                        acc.x ^= v.x; acc.y ^= v.y; acc.z ^= v.z; acc.w ^= v.w;
+                    }
+                    *reinterpret_cast<uint4 *>(out + size_t(u) * p.S + qd * 16) = acc;
+                }
+            }
+            __syncwarp();
+            lap(5);
+        }
+        if (p.phase_cycles && lane == 0) atomicAdd(&p.phase_cycles[6], 1ull);
+        if (defer) {
+            if (lane == 0) q.list_out[atomicAdd(q.count_out, 1u)] = (unsigned int)cw;
+            __syncwarp();
+            continue;
+        }
+        if (lane == 0) {
+            atomicAdd(&p.stats[3], 1ull);
+            if (ok) {
+                if (p.fail) p.fail[cw] = 0;
+                if (hdr[3] != 0u) atomicAdd(&p.stats[5], 1ull);   // a frame the peel kernel counted as an error
+            } else {
+                atomicAdd(&p.stats[4], 1ull);
+            }
+        }
+        __syncwarp();
+    }
+}
+
 // ---- host side -------------------------------------------------------------------------------
 struct HybridScratch {
     uint8_t *d_full = nullptr;          // [max_batch][n][S]
     unsigned int *d_list = nullptr;     // [max_batch] stalled codewords, written by the peel kernel
-    unsigned int *d_list2 = nullptr, *d_list3 = nullptr;   // deferred by warp stage 1 / stage 2
-    unsigned int *d_count = nullptr;    // [8]: list counts [0..2], work counters [3..4]
-    int wpc[2] = {0, 0}, slot_words[2] = {0, 0};            // the two warp stages: warps per CTA, words per slot
+    unsigned int *d_list2 = nullptr, *d_list3 = nullptr, *d_list4 = nullptr;   // deferred by warp stages 0 / 1 / 2
+    unsigned int *d_count = nullptr;    // [8]: list counts [0..3], work counters [4..6]
+    // warp stages: [0] inactivation, typical slots; [1] inactivation, worst-case slots; [2] per-warp Gauss-Jordan
+    int wpc[3] = {0, 0, 0}, slot_words[3] = {0, 0, 0};
+    int wpc_pat = 0, slot_words_pat = 0;                     // stage 0 without payload (error-rate runs): smaller slots
     uint32_t *d_gmat = nullptr;         // per-CTA matrices when they do not fit in shared memory
     int grid = 0, smem = 0, RSW = 0;
     bool ready = false;
@@ -474,7 +841,7 @@ struct HybridScratch {
 
 inline void hybrid_free(HybridScratch &h)
 {
-    cudaFree(h.d_full); cudaFree(h.d_list); cudaFree(h.d_list2); cudaFree(h.d_list3); cudaFree(h.d_count); cudaFree(h.d_gmat);
+    cudaFree(h.d_full); cudaFree(h.d_list); cudaFree(h.d_list2); cudaFree(h.d_list3); cudaFree(h.d_list4); cudaFree(h.d_count); cudaFree(h.d_gmat);
     h = HybridScratch();
 }
 
@@ -492,21 +859,34 @@ inline int hybrid_prepare(HybridScratch &h, const HostCode &code, int S, int NW,
     if ((e = cudaMalloc(&h.d_list, size_t(max_batch) * 4)) != cudaSuccess) return bad("hybrid: list", e);
     if ((e = cudaMalloc(&h.d_list2, size_t(max_batch) * 4)) != cudaSuccess) return bad("hybrid: list", e);
     if ((e = cudaMalloc(&h.d_list3, size_t(max_batch) * 4)) != cudaSuccess) return bad("hybrid: list", e);
+    if ((e = cudaMalloc(&h.d_list4, size_t(max_batch) * 4)) != cudaSuccess) return bad("hybrid: list", e);
     if ((e = cudaMalloc(&h.d_count, 8 * 4)) != cudaSuccess) return bad("hybrid: count", e);
-    {   // warp stages: stage 1 sized for a typical stopping set (3/4 of the checks involved), stage 2 for the worst case
+    {   // warp stages: [0] inactivation decoding, slots for a typical stopping set (2/3 of the checks involved);
+        //              [1] the same with worst-case slots, for what [0] defers for size;
+        //              [2] plain Gauss-Jordan per warp, worst-case slots: more than kInactMax inactivations
         const long long budget_w = (long long)(smem_optin - 2048) / 4;
-        const int fixed = ge_warp_fixed_words(code.m, NW);
-        const int typ = 3 * code.m / 4;
-        long long s1 = fixed + ge_warp_matrix_words(typ, typ, true);
-        long long s2 = fixed + ge_warp_matrix_words(code.m, code.m, true);
-        int w1 = int(std::max<long long>(1, std::min<long long>(16, budget_w / s1)));
-        int w2 = int(std::max<long long>(1, std::min<long long>(16, budget_w / s2)));
-        if (const char *ev = getenv("LDPC_CUDA_GE_WPC")) w1 = std::max(1, std::min(16, atoi(ev)));
-        w2 = std::min(w2, w1);
-        h.wpc[0] = w1; h.slot_words[0] = int((budget_w / w1) & ~3ll);
-        h.wpc[1] = w2; h.slot_words[1] = int((budget_w / w2) & ~3ll);
-        if (h.slot_words[0] <= fixed + 64 || h.slot_words[1] <= fixed + 64) { h.wpc[0] = h.wpc[1] = 0; }   // CTA kernel only
+        const int typ = 2 * code.m / 3;
+        const int fx = ge_inact_fixed_words(code.m, NW, MW);
+        const long long need[3] = {fx + ge_inact_area_words(typ, typ, code.VW, true),
+                                   fx + ge_inact_area_words(code.m, code.m, code.VW, true),
+                                   ge_warp_fixed_words(code.m, NW) + ge_warp_matrix_words(code.m, code.m, true)};
+        for (int i = 0; i < 3; i++) {
+            int w = int(std::max<long long>(1, std::min<long long>(16, budget_w / need[i])));
+            if (i == 0)
+                if (const char *ev = getenv("LDPC_CUDA_GE_WPC")) w = std::max(1, std::min(16, atoi(ev)));
+            h.wpc[i] = w;
+            h.slot_words[i] = int((budget_w / w) & ~3ll);
+            if (i != 0 && h.slot_words[i] < need[i]) h.wpc[i] = 0;                  // worst case does not fit: stage skipped
+        }
+        if (h.slot_words[0] <= fx + 64) h.wpc[0] = 0;
+        if (h.wpc[1] >= h.wpc[0] && h.wpc[0] > 0) { h.wpc[0] = h.wpc[1]; h.slot_words[0] = h.slot_words[1]; h.wpc[1] = 0; }   // no need for two sizes
+        const long long sp = fx + ge_inact_area_words(code.m, code.m, code.VW, false);
+        h.wpc_pat = int(std::max<long long>(1, std::min<long long>(16, budget_w / sp)));
+        h.slot_words_pat = int((budget_w / h.wpc_pat) & ~3ll);
+        if (h.wpc[0] == 0 || h.slot_words_pat < sp) h.wpc_pat = 0;
         if ((e = cudaFuncSetAttribute(hybrid_ge_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin - 1024)) != cudaSuccess)
+            return bad("hybrid: cudaFuncSetAttribute", e);
+        if ((e = cudaFuncSetAttribute(hybrid_inact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin - 1024)) != cudaSuccess)
             return bad("hybrid: cudaFuncSetAttribute", e);
     }
     h.RSW = 2 * MW + 1;

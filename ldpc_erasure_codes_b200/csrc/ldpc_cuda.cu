@@ -55,8 +55,9 @@ static int allow_max_smem(const void *func, int smem_optin)
     return LDPC_OK;
 }
 
-// LDPC_CUDA_GE_CTA_ONLY=1: elimination stage uses the CTA-per-codeword kernel only (tests compare both paths)
-static bool ge_cta_only() { const char *e = getenv("LDPC_CUDA_GE_CTA_ONLY"); return e && *e && *e != '0'; }
+// LDPC_CUDA_GE_STAGES: bit 0 = inactivation stage, bit 1 = per-warp elimination stage (default 3); the
+// CTA-per-codeword kernel always runs last on what is left.  Tests use it to compare the solvers.
+static int ge_stage_mask() { const char *e = getenv("LDPC_CUDA_GE_STAGES"); return e && *e ? atoi(e) : 3; }
 
 // LDPC_CUDA_DEBUG_SYNC=1: synchronise after every launch so that a faulting kernel is named
 static int debug_sync(const char *what, cudaStream_t st)
@@ -341,8 +342,8 @@ extern "C" int ldpc_ctx_create(ldpc_ctx **out, const char *h_mat_path, int code_
     CTX_TRY(cudaMalloc(&c->d_work_ctr, sizeof(unsigned int)));
     if (const char *e = getenv("LDPC_CUDA_PHASE_TIMING")) {
         if (*e && *e != '0') {
-            CTX_TRY(cudaMalloc(&c->d_phase, 8 * sizeof(unsigned long long)));
-            CTX_TRY(cudaMemset(c->d_phase, 0, 8 * sizeof(unsigned long long)));
+            CTX_TRY(cudaMalloc(&c->d_phase, 16 * sizeof(unsigned long long)));
+            CTX_TRY(cudaMemset(c->d_phase, 0, 16 * sizeof(unsigned long long)));
         }
     }
 #undef CTX_TRY
@@ -612,24 +613,30 @@ static int decode_chunk(ldpc_ctx *c, const uint8_t *d_cw, const uint32_t *d_mask
         GeParams gp;
         gp.mask = d_mask; gp.sched = sched; gp.list = c->hyb.d_list; gp.list_count = c->hyb.d_count;
         gp.full = pattern_only ? nullptr : c->hyb.d_full; gp.out = d_out; gp.fail = pp.fail; gp.stats = c->d_stats; gp.cidx = c->d_cidx;
-        gp.gmat = c->hyb.d_gmat; gp.n = c->code.n; gp.k = c->code.k; gp.m = c->code.m; gp.RW = c->code.RW; gp.NW = c->NW;
+        gp.vadj = c->d_vadj; gp.VW = c->code.VW; gp.phase_cycles = c->d_phase ? c->d_phase + 8 : nullptr; gp.gmat = c->hyb.d_gmat; gp.n = c->code.n; gp.k = c->code.k; gp.m = c->code.m; gp.RW = c->code.RW; gp.NW = c->NW;
         gp.MW = c->MW; gp.S = c->S; gp.stride = c->sched_stride; gp.RSW = c->hyb.RSW;
-        // warp-per-codeword stages first; what does not fit their shared-memory slots falls through
-        const unsigned int *lists[3] = {c->hyb.d_list, c->hyb.d_list2, c->hyb.d_list3};
+        // warp-per-codeword stages first (inactivation decoding with typical, then worst-case slots; then plain
+        // elimination per warp); what they defer falls through to the CTA-per-codeword kernel
+        const unsigned int *lists[4] = {c->hyb.d_list, c->hyb.d_list2, c->hyb.d_list3, c->hyb.d_list4};
         int li = 0;
-        for (int sg = 0; sg < 2 && c->hyb.wpc[sg] > 0 && !ge_cta_only(); sg++) {
-            if (sg == 1 && c->hyb.wpc[1] == c->hyb.wpc[0]) break;    // same slots: nothing more would fit
+        const int stage_mask = ge_stage_mask();
+        for (int sg = 0; sg < 3; sg++) {
+            if (c->hyb.wpc[sg] <= 0 || !((stage_mask >> (sg == 2 ? 1 : 0)) & 1)) continue;
             GeWarpParams wp;
             wp.g = gp; wp.g.list = lists[li]; wp.g.list_count = c->hyb.d_count + li;
             wp.list_out = const_cast<unsigned int *>(lists[li + 1]); wp.count_out = c->hyb.d_count + li + 1;
-            wp.work_ctr = c->hyb.d_count + 3 + sg; wp.slot_words = c->hyb.slot_words[sg];
-            ProfScope ps(c, LDPC_K_HYBRID, st);
-            hybrid_ge_warp_kernel<<<c->num_sms, 32 * c->hyb.wpc[sg], size_t(c->hyb.wpc[sg]) * c->hyb.slot_words[sg] * 4, st>>>(wp);
+            int wpc = c->hyb.wpc[sg], slot = c->hyb.slot_words[sg];
+            if (sg == 0 && pattern_only && c->hyb.wpc_pat > 0) { wpc = c->hyb.wpc_pat; slot = c->hyb.slot_words_pat; }
+            wp.work_ctr = c->hyb.d_count + 4 + sg; wp.slot_words = slot;
+            const size_t smem = size_t(wpc) * slot * 4;
+            ProfScope ps(c, sg < 2 ? LDPC_K_HYBRID : LDPC_K_HYBRID_WARP, st);
+            if (sg < 2) hybrid_inact_kernel<<<c->num_sms, 32 * wpc, smem, st>>>(wp);
+            else hybrid_ge_warp_kernel<<<c->num_sms, 32 * wpc, smem, st>>>(wp);
             li++;
         }
         gp.list = lists[li]; gp.list_count = c->hyb.d_count + li;
         {
-            ProfScope ps(c, LDPC_K_HYBRID, st);
+            ProfScope ps(c, LDPC_K_HYBRID_CTA, st);
             if (gp.gmat) hybrid_ge_kernel<true><<<c->hyb.grid, kGeThreads, c->hyb.smem, st>>>(gp);
             else hybrid_ge_kernel<false><<<c->hyb.grid, kGeThreads, c->hyb.smem, st>>>(gp);
         }
@@ -730,7 +737,8 @@ extern "C" int ldpc_profile_read(ldpc_ctx *c, ldpc_profile *out, int reset)
     for (int i = 0; i < LDPC_K_KINDS; i++) out->launches[i] = c->launches[i];
     if (c->d_phase) {
         CUDA_TRY(cudaMemcpy(out->exec_phase_cycles, c->d_phase, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-        if (reset) CUDA_TRY(cudaMemset(c->d_phase, 0, 8 * sizeof(unsigned long long)));
+        CUDA_TRY(cudaMemcpy(out->ge_phase_cycles, c->d_phase + 8, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        if (reset) CUDA_TRY(cudaMemset(c->d_phase, 0, 16 * sizeof(unsigned long long)));
     }
     if (reset) {
         for (auto &r : c->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }

@@ -313,13 +313,14 @@ def test_hybrid_n4000_bursty_stress(codecs):
 
 
 def test_hybrid_warp_and_cta_kernels_agree(codecs, monkeypatch):
-    """The warp-per-codeword stages and the CTA-per-codeword kernel are two solvers of the same system."""
+    """Inactivation decoding, per-warp elimination and the CTA-per-codeword kernel solve the same systems."""
     codec = codecs(1, 64)
     code, cw, rx, mask, flags = _scenario(codec, 1, 300, 13, 4711, 64)
     ref = _hybrid_check(codec, code, rx, mask, flags)
     assert (ref["status"] == 1).sum() > 40
-    monkeypatch.setenv("LDPC_CUDA_GE_CTA_ONLY", "1")
-    _hybrid_check(codec, code, rx, mask, flags)
+    for stages in ("0", "2", "1"):          # CTA kernel only / per-warp elimination / inactivation decoding
+        monkeypatch.setenv("LDPC_CUDA_GE_STAGES", stages)
+        _hybrid_check(codec, code, rx, mask, flags)
 
 
 @pytest.mark.parametrize("wpc", ["16", "7"])
