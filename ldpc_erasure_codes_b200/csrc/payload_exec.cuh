@@ -204,53 +204,86 @@ payload_exec_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
             }
             t_dst = base_a + v * W;
         };
-        auto works = [&](int l, int cnt) { return ((wg + l) % WPGc) * EPW < cnt; };
-        auto setup = [&](int l) {                     // my lane group's first entry in level l (my warp works there)
-            const int s0 = lvo[l];
-            t_end = lvo[l + 1];
+        // My warp's tasks (the levels it works in) are found 32 levels at a time with one ballot: lane i
+        // looks at level l0+i.  Walking the level table entry by entry costs two dependent shared loads
+        // per level and warp, which is as long as the work itself when the levels are small.
+        constexpr unsigned FULLM = 0xFFFFFFFFu;
+        const int wl = tg & 31;
+        int l0 = -32;                                 // first level of the current chunk
+        unsigned todo = 0u;                           // levels of the chunk where my warp still has to work
+        int c_s0 = 0, c_s1 = 0;                       // lane i: entry range of level l0+i
+        uint32_t c_dt = 0, done_base = 0;             // lane i: workers of all levels below l0+i; below the next chunk
+        uint32_t done_target = 0;
+        auto next_task = [&]() -> bool {              // warp-uniform; sets up t_* for my lane group
+            while (!todo) {
+                l0 += 32;
+                if (l0 >= nl) return false;
+                const int ll = l0 + wl;
+                c_s0 = 0; c_s1 = 0;
+                if (ll < nl) { c_s0 = lvo[ll]; c_s1 = lvo[ll + 1]; }
+                const int cnt = c_s1 - c_s0;
+                const int nw = ll < nl ? min(WPGc, (cnt + EPW - 1) / EPW) : 0;
+                int inc = nw;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(FULLM, inc, o);
+                    if (wl >= o) inc += t;
+                }
+                c_dt = done_base + uint32_t(inc - nw);
+                done_base += uint32_t(__shfl_sync(FULLM, inc, 31));
+                todo = __ballot_sync(FULLM, ll < nl && ((wg + ll) % WPGc) * EPW < cnt);
+            }
+            const int b = __ffs(todo) - 1;
+            todo &= todo - 1u;
+            const int l = l0 + b;
+            const int s0 = __shfl_sync(FULLM, c_s0, b);
+            t_end = __shfl_sync(FULLM, c_s1, b);
+            done_target = __shfl_sync(FULLM, c_dt, b);
             t_idx = s0 + ((wg + l) % WPGc) * EPW + es;
             t_valid = t_idx < t_end;
             if (t_valid) prepare();
+            return true;
         };
-        int prepared_lvl = -1;
-        uint32_t done_target = 0;                     // workers of all levels below the current one
-        for (int l = 0; l < nl; l++) {
-            const int cnt = int(lvo[l + 1]) - int(lvo[l]);
-            const int nw = min(WPGc, (cnt + EPW - 1) / EPW);
-            if (works(l, cnt)) {
-                if (prepared_lvl != l) setup(l);
-                if (done_target) {                    // wait for the levels below
-                    uint32_t seen, spins = 0;
-                    do {
-                        asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(seen) : "r"(done_a) : "memory");
-                        if (++spins > (1u << 26)) {   // a lost hand-off must trap, not hang the GPU
-                            printf("libldpc_cuda: level hand-off timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
-                            __trap();
-                        }
-                    } while (seen < done_target);
-                }
-                while (t_valid) {
-                    uint4 val[RWM];
-#pragma unroll
-                    for (int t = 0; t < RWM; t++) val[t] = lds128(t_src[t]);
-#pragma unroll
-                    for (int st = 1; st < RWM; st <<= 1)           // XOR tree
-#pragma unroll
-                        for (int t = 0; t + st < RWM; t += 2 * st) xor_acc(val[t], val[t + st]);
-                    sts128(t_dst, val[0]);
-                    t_idx += NGROUPS;                  // another pass in this level?
-                    t_valid = t_idx < t_end;
-                    if (t_valid) prepare();
-                }
-                __syncwarp();
-                if ((tg & 31) == 0)
-                    asm volatile("red.release.cta.shared::cta.add.u32 [%0], %1;" ::"r"(done_a), "r"(1u) : "memory");
-                // off the critical path: find my warp's next level and prepare its first pass
-                for (int l2 = l + 1; l2 < nl; l2++) {
-                    if (works(l2, int(lvo[l2 + 1]) - int(lvo[l2]))) { setup(l2); prepared_lvl = l2; break; }
-                }
+        bool have = next_task();
+        const bool timed = p.phase_cycles != nullptr && wl == 0;
+        long long tk0 = 0, tk_spin = 0, tk_exec = 0, tk_prep = 0;
+        while (have) {
+            if (timed) tk0 = clock64();
+            if (done_target) {                        // wait for the levels below
+                uint32_t seen, spins = 0;
+                do {
+                    asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(seen) : "r"(done_a) : "memory");
+                    if (++spins > (1u << 26)) {       // a lost hand-off must trap, not hang the GPU
+                        printf("libldpc_cuda: level hand-off timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+                        __trap();
+                    }
+                } while (seen < done_target);
             }
-            done_target += uint32_t(nw);
+            if (timed) { const long long t = clock64(); tk_spin += t - tk0; tk0 = t; }
+            while (t_valid) {
+                uint4 val[RWM];
+#pragma unroll
+                for (int t = 0; t < RWM; t++) val[t] = lds128(t_src[t]);
+#pragma unroll
+                for (int st = 1; st < RWM; st <<= 1)               // XOR tree
+#pragma unroll
+                    for (int t = 0; t + st < RWM; t += 2 * st) xor_acc(val[t], val[t + st]);
+                sts128(t_dst, val[0]);
+                t_idx += NGROUPS;                      // another pass in this level?
+                t_valid = t_idx < t_end;
+                if (t_valid) prepare();
+            }
+            __syncwarp();
+            if (wl == 0)
+                asm volatile("red.release.cta.shared::cta.add.u32 [%0], %1;" ::"r"(done_a), "r"(1u) : "memory");
+            if (timed) { const long long t = clock64(); tk_exec += t - tk0; tk0 = t; }
+            have = next_task();                        // off the critical path: my next level, addresses prepared
+            if (timed) { const long long t = clock64(); tk_prep += t - tk0; }
+        }
+        if (timed) {   // [5] spin, [6] gather+store+release, [7] next-task preparation: cycles summed over the group's warps
+            atomicAdd(&p.phase_cycles[5], (unsigned long long)tk_spin);
+            atomicAdd(&p.phase_cycles[6], (unsigned long long)tk_exec);
+            atomicAdd(&p.phase_cycles[7], (unsigned long long)tk_prep);
         }
 
         // ---- store the first rows_out rows, recycle the slot --------------------------------
