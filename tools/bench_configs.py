@@ -49,8 +49,10 @@ def ldpc_case(name, ci, S, B, chan, mode="peel", max_iter=50, reps=3, do_encode=
         codec.decode(cw, mask, max_iter=max_iter, mode=mode, out=out, fail=fail)
     pr = codec.profile_read(reset=True); codec.profile_enable(False)
     st = codec.stats()
-    ms_parts = {kk: round(pr[kk]["ms"] / reps, 3) for kk in ("peel", "exec_decode", "hybrid")}
-    ms = sum(ms_parts.values())
+    ms_parts = {kk: round(pr[kk]["ms"] / reps, 3) for kk in ("peel", "exec_decode")}
+    ms_parts["hybrid"] = round(sum(pr[kk]["ms"] for kk in ("hybrid", "hybrid_warp", "hybrid_cta")) / reps, 3)   # all elimination stages
+    ms_parts["hybrid_stages"] = [round(pr[kk]["ms"] / reps, 3) for kk in ("hybrid", "hybrid_warp", "hybrid_cta")]
+    ms = ms_parts["peel"] + ms_parts["exec_decode"] + ms_parts["hybrid"]
     alg = (n * S + (n + 7) // 8 + k * S + 1) * B
     emit(config=name, op="decode", mode=mode, code=ci, S=S, B=B, channel={k_: (list(v) if isinstance(v, tuple) else v) for k_, v in chan.items()},
          max_iter=max_iter, erasure_rate=round(float(torch.tensor(0.0) + sum(bin(x & 0xFFFFFFFF).count("1") for x in mask[:64].flatten().tolist()) / (64 * n)), 4),
