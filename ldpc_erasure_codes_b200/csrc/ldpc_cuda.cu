@@ -199,8 +199,8 @@ static int choose_geom(const ldpc_ctx *c, bool dynamic_sched, ExecGeom *g)
     const int blob = sched_blob_max_bytes(c->code.m);
     const int fixed = cidx_bytes + 128 + 128 + 64 + 128 + 128;
     ExecGeom best;
-    for (int W = std::min(S, 64); W >= 16; W >>= 1) {
-        if (S % W) continue;
+    for (int W = 64; W >= 16; W >>= 1) {         // instantiated slice widths; S is a multiple of 16, so 16 always divides
+        if (W > S || S % W) continue;
         if (c->force_W && W != c->force_W) continue;
         const int slot = ((n + kBoxRows - 1) / kBoxRows) * kBoxRows * W;
         int nslot;

@@ -240,6 +240,85 @@ def test_large_batch_round_trip_properties(codecs):
     codec.close()
 
 
+# ------------------------------------------------------------------------------- a code the user brings
+def _random_h(n, m, dv, tri, seed):
+    """Sparse H: [random part | lower-triangular (tri) or random parity part], column weight ~dv."""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(seed)
+    k = n - m
+    H = np.zeros((m, n), np.uint8)
+    for v in range(k):
+        H[rng.choice(m, dv, replace=False), v] = 1
+    for r in range(m):
+        if tri:
+            H[r, k + r] = 1
+            if r:
+                lo = max(0, r - 6)                  # banded: keeps the column weights small
+                H[r, k + lo + rng.choice(r - lo, min(r - lo, 2), replace=False)] = 1
+        else:
+            H[rng.choice(m, dv, replace=False), k + r] = 1
+    for r in range(m):                       # no empty rows
+        if not H[r, :k].any():
+            H[r, rng.integers(k)] = 1
+    return sp.csc_matrix(H.astype(np.float64))
+
+
+@pytest.mark.parametrize("n,m,S", [(96, 48, 16), (333, 100, 48), (1000, 250, 64)])
+def test_user_supplied_triangular_code(tmp_path, n, m, S):
+    """ldpc_ctx_create(path): a MAT-v5 file that is not one of the built-ins; encode, erase, peel and hybrid decode."""
+    import scipy.io as sio
+    from ldpc_erasure_codes_b200.codec import LdpcCodec
+    H = _random_h(n, m, 3, True, seed=n)
+    path = str(tmp_path / "user_code.mat")
+    sio.savemat(path, {"H_sparse": H}, do_compression=True)
+    codec = LdpcCodec(code=path, symbol_bytes=S, device=0, max_batch=128)
+    assert (codec.n, codec.k, codec.m) == (n, n - m, m)
+    code = orc.Code(H)
+    B = 77
+    info = _rand_info(B, codec.k, S, seed=n)
+    cw = codec.encode(info)
+    assert np.array_equal(_np(cw), orc.encode(code, _np(info)))
+    for P, mode, it in ((8, "peel", 50), (20, "peel", 3), (18, "hybrid", 10)):
+        rx = cw.clone()
+        mask = codec.gen_erasures(B, 31 + P, P=P, payload=rx)
+        flags = orc.gen_erasures_iid(n, 31 + P, B, P=P)
+        out, fail = codec.decode(rx, mask, max_iter=it, mode=mode)
+        ref = orc.decode(code, _np(rx), flags, max_iter=it, mode=mode)
+        assert np.array_equal(_np(fail), ref["fail_sys"]) and np.array_equal(_np(out), ref["out"])
+    codec.close()
+
+
+def test_user_supplied_non_triangular_code_decodes_but_does_not_encode(tmp_path):
+    import scipy.io as sio
+    from ldpc_erasure_codes_b200 import _lib as L
+    from ldpc_erasure_codes_b200.codec import LdpcCodec
+    n, m, S = 200, 80, 32
+    H = _random_h(n, m, 3, False, seed=5)
+    path = str(tmp_path / "user_code.mat")
+    sio.savemat(path, {"H_sparse": H})
+    codec = LdpcCodec(code=path, symbol_bytes=S, device=0, max_batch=64)
+    info = _rand_info(4, codec.k, S, seed=1)
+    with pytest.raises(L.LdpcCudaError) as ei:
+        codec.encode(info)
+    assert ei.value.code == -7                                  # LDPC_ERR_NOT_TRIANGULAR
+    code = orc.Code(H)
+    rx = _rand_info(40, n, S, seed=2)                           # arbitrary words: the replay is exact on any input
+    mask = codec.gen_erasures(40, 9, P=10, payload=rx)
+    flags = orc.gen_erasures_iid(n, 9, 40, P=10)
+    out, fail = codec.decode(rx, mask, max_iter=50, mode="peel")
+    ref = orc.decode(code, _np(rx), flags, max_iter=50, mode="peel")
+    assert np.array_equal(_np(fail), ref["fail_sys"]) and np.array_equal(_np(out), ref["out"])
+    codec.close()
+
+
+def test_hybrid_reference_symbol_size(codecs):
+    """S = 1024 (the reference's 128 x u64 symbols): the elimination stage walks the payload 64 bytes at a time."""
+    codec = codecs(1, 1024, 64)
+    code, cw, rx, mask, flags = _scenario(codec, 1, 24, 13, 2025, 1024)
+    ref = _hybrid_check(codec, code, rx, mask, flags)
+    assert (ref["status"] == 1).sum() > 2
+
+
 # ------------------------------------------------------------------------------- hybrid-ML (GF(2) elimination)
 def _hybrid_check(codec, code, rx, mask, flags, max_iter=10):
     codec.reset_stats()
