@@ -435,7 +435,7 @@ def test_rs_generator_matches_oracle(rs_codecs, nk):
     assert np.array_equal(rs_codecs(n, k, 16).generator(), orc.rs_gsys(n, k))
 
 
-@pytest.mark.parametrize("n,k,S", [(255, 191, 1024), (255, 192, 64), (7, 5, 16)])
+@pytest.mark.parametrize("n,k,S", [(255, 191, 1024), (255, 192, 64), (7, 5, 16), (250, 125, 48), (100, 90, 80)])
 def test_rs_encode_bit_exact(rs_codecs, n, k, S):
     codec = rs_codecs(n, k, S)
     info = _rand_info(5, k, S, seed=n + k)
@@ -445,7 +445,8 @@ def test_rs_encode_bit_exact(rs_codecs, n, k, S):
         assert np.array_equal(cw[b], orc.rs_encode(G, _np(info)[b]))
 
 
-@pytest.mark.parametrize("n,k,S,p", [(255, 191, 1024, 0.2), (255, 192, 64, 0.2), (255, 191, 64, 0.05), (7, 5, 16, 0.25)])
+@pytest.mark.parametrize("n,k,S,p", [(255, 191, 1024, 0.2), (255, 192, 64, 0.2), (255, 191, 64, 0.05), (7, 5, 16, 0.25),
+                                     (250, 125, 48, 0.45), (100, 90, 80, 0.08)])
 def test_rs_decode_bit_exact(rs_codecs, n, k, S, p):
     """Decoder == restated Matlab/My_RS_Decode_Optimize_With_GFTables.m on the first k received symbols."""
     from ldpc_erasure_codes_b200.codec import pack_mask
@@ -500,3 +501,28 @@ def test_simulate_fer_matches_explicit_decode_and_oracle(codecs, mode, max_iter)
     assert sim["ldpc_errors"] - sim["ml_recovered"] == int(ref["fail_sys"].sum()) == int(_np(fail).sum())
     assert sim["rs_errors"] == sum(orc.rs_mds_count(code.n, 255, 192, f) for f in flags)
     assert not _np(out).any()           # the all-zero codeword decodes to zeros
+
+
+def test_simulate_fer_bursty_channel_and_host_hybrid(codecs):
+    """The two-state channel through the counters-only run, and the hybrid decoder through the host-buffer entry point."""
+    from ldpc_erasure_codes_b200.codec import unpack_mask
+    codec = codecs(1, 32)
+    code = orc.Code.builtin(1)
+    B, seed, chan = 300, 77, (0.02, 0.08, 10.0)
+    codec.reset_stats()
+    codec.simulate_fer(B, seed, bursty=chan, max_iter=10, mode="hybrid")
+    sim = codec.stats()
+    mask = codec.gen_erasures(B, seed, bursty=chan)
+    flags = unpack_mask(mask, code.n)
+    assert np.array_equal(flags, orc.gen_erasures_bursty(code.n, seed, B, *chan)[0])
+    ref = orc.decode(code, np.zeros((B, code.n, 32), np.uint8), flags, max_iter=10, mode="hybrid")
+    assert sim["frames"] == B and sim["ml_attempts"] == int((ref["status"] > 0).sum())
+    assert sim["ldpc_errors"] - sim["ml_recovered"] == int(ref["fail_sys"].sum())
+    # host buffers in, host buffers out, hybrid mode
+    info = _rand_info(B, codec.k, 32, seed=5)
+    cw = codec.encode(info)
+    rx = cw.clone()
+    mask = codec.gen_erasures(B, seed, bursty=chan, payload=rx)
+    out_h, fail_h = codec.decode_host(rx.cpu().pin_memory(), mask.cpu().pin_memory(), max_iter=10, mode="hybrid")
+    ref = orc.decode(code, _np(rx), flags, max_iter=10, mode="hybrid")
+    assert np.array_equal(out_h.numpy(), ref["out"]) and np.array_equal(fail_h.numpy(), ref["fail_sys"])
