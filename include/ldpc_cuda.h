@@ -174,10 +174,11 @@ int ldpc_reset_stats(ldpc_ctx *ctx);
  * launching stream; ldpc_profile_read() synchronises and returns per-kernel device time.
  * Launch counters are always maintained.                                                 */
 enum { LDPC_K_PEEL = 0, LDPC_K_EXEC_DECODE = 1, LDPC_K_EXEC_ENCODE = 2,
-       LDPC_K_HYBRID = 3,        /* elimination stage 1: inactivation decoding, one warp per codeword       */
+       LDPC_K_HYBRID = 3,        /* elimination stage 1: inactivation decoding, one warp per codeword (pattern part) */
        LDPC_K_CHANNEL = 4,
        LDPC_K_HYBRID_WARP = 5,   /* stage 2: per-warp Gauss-Jordan on what stage 1 deferred (rare)          */
        LDPC_K_HYBRID_CTA = 6,    /* stage 3: CTA-per-codeword Gauss-Jordan on what stage 2 deferred         */
+       LDPC_K_HYBRID_APPLY = 7,  /* stage 1, payload part: replay of the recorded pivots                    */
        LDPC_K_KINDS = 8 };
 typedef struct ldpc_profile {
     double ms[LDPC_K_KINDS];        /* summed device time per kernel kind (profiling on)  */
@@ -188,6 +189,7 @@ typedef struct ldpc_profile {
     uint64_t exec_phase_cycles[8];
     uint64_t ge_phase_cycles[8];    /* LDPC_CUDA_PHASE_TIMING=1: inactivation stage, warp cycles per phase: setup, rows,
                                        adjacency+syndromes, peel/inactivate, dense solve, output; [6] = codewords      */
+    uint64_t apply_phase_cycles[8]; /* apply kernel: plan load, right-hand sides, replay, dense solve, output; [6] = codewords */
 } ldpc_profile;
 int ldpc_profile_enable(ldpc_ctx *ctx, int on);
 int ldpc_profile_read(ldpc_ctx *ctx, ldpc_profile *out, int reset);

@@ -40,11 +40,11 @@ class Stats(C.Structure):
 
 
 K_KINDS = 8
-KIND_NAMES = ["peel", "exec_decode", "exec_encode", "hybrid", "channel", "hybrid_warp", "hybrid_cta", "k7"]
+KIND_NAMES = ["peel", "exec_decode", "exec_encode", "hybrid", "channel", "hybrid_warp", "hybrid_cta", "hybrid_apply"]
 
 
 class Profile(C.Structure):
-    _fields_ = [("ms", C.c_double * K_KINDS), ("launches", C.c_int64 * K_KINDS), ("exec_phase_cycles", C.c_uint64 * 8), ("ge_phase_cycles", C.c_uint64 * 8)]
+    _fields_ = [("ms", C.c_double * K_KINDS), ("launches", C.c_int64 * K_KINDS), ("exec_phase_cycles", C.c_uint64 * 8), ("ge_phase_cycles", C.c_uint64 * 8), ("apply_phase_cycles", C.c_uint64 * 8)]
 
 
 _lib = None

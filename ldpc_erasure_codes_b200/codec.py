@@ -169,6 +169,7 @@ class LdpcCodec:
         d = {name: dict(ms=p.ms[i], launches=p.launches[i]) for i, name in enumerate(_lib.KIND_NAMES)}
         d["exec_phase_cycles"] = list(p.exec_phase_cycles)
         d["ge_phase_cycles"] = list(p.ge_phase_cycles)
+        d["apply_phase_cycles"] = list(p.apply_phase_cycles)
         return d
 
 

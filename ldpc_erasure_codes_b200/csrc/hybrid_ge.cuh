@@ -37,7 +37,8 @@ struct GeParams {
     const uint8_t *sched;            // schedule blobs: the symbols peeling recovered
     const unsigned int *list;        // codewords that still have erasures
     const unsigned int *list_count;
-    const uint8_t *full;             // [B][n][S] every symbol after peeling (valid for listed codewords)
+    const uint8_t *synd;             // [B][m][S] per check: XOR of the members known after peeling (from the executor;
+                                     // valid for listed codewords), or nullptr = error-rate run, pattern only
     uint8_t *out;                    // [B][k][S]
     uint8_t *fail;                   // [B]
     unsigned long long *stats;       // [3] ml_attempts, [4] ml_failures, [5] ml_recovered
@@ -53,6 +54,33 @@ struct GeParams {
 __host__ __device__ inline size_t ge_small_bytes(int m, int NW)
 {   // er[NW] pref[NW+1] prow[RSW<=257] varlist[m] pivrow[m] used[m] inv[m] + scalars, generously rounded
     return size_t(NW) * 4 + size_t(NW + 1) * 4 + 260 * 4 + size_t(m) * 2 * 2 + size_t(m) * 2 + 64 + 64;
+}
+
+
+// 16 bytes (quarter qd of the 64-byte chunk at ch) of check r's right-hand side
+__device__ __forceinline__ uint4 ge_rhs_quarter(const GeParams &p, long long cw, int r, int ch, int qd)
+{
+    return *reinterpret_cast<const uint4 *>(p.synd + (size_t(cw) * p.m + r) * p.S + ch + qd * 16);
+}
+
+// A warp loads the right-hand sides of its R rows: 8 rows x 4 quarters per instruction, four instructions in flight.
+__device__ __forceinline__ void ge_load_rhs(const GeParams &p, long long cw, const uint16_t *rowmap, int R, int ch, int nq,
+                                            uint32_t *bmat, int pitch, int lane)
+{
+    const int qd = lane & 3, hs = lane >> 2;
+    for (int r0 = hs; r0 < R; r0 += 32) {
+        uint4 v[4];
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            const int ri = r0 + 8 * t;
+            v[t] = (ri < R && qd < nq) ? ge_rhs_quarter(p, cw, rowmap[ri], ch, qd) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            const int ri = r0 + 8 * t;
+            if (ri < R) *reinterpret_cast<uint4 *>(bmat + size_t(ri) * pitch + qd * 4) = v[t];
+        }
+    }
 }
 
 template <bool GMAT>   // where [A | I] lives: per-CTA global workspace (true) or shared memory (false)
@@ -160,22 +188,14 @@ __global__ void __launch_bounds__(kGeThreads) hybrid_ge_kernel(const GeParams p)
             }
         }
         // ---- 4. payload: syndromes, then every erased systematic symbol -----------------------
-        if (ok && p.full) {   // (full == nullptr: error-rate run, pattern only)
-            const uint8_t *full = p.full + size_t(cw) * p.n * p.S;
+        if (ok && p.synd) {   // (synd == nullptr: error-rate run, pattern only)
             uint8_t *out = p.out + size_t(cw) * p.k * p.S;
             const int qd = tid & 3;             // 16-byte quarter of a 64-byte chunk
             for (int ch = 0; ch < p.S; ch += 64) {
                 const int cb = min(64, p.S - ch);   // S is a multiple of 16
                 for (int r = tid >> 2; r < m; r += kGeThreads / 4) {
                     if (!inv[r] || qd * 16 >= cb) continue;
-                    uint4 acc = make_uint4(0u, 0u, 0u, 0u);
-                    for (int j = 0; j < RW; j++) {
-                        const uint32_t u = p.cidx[r * RW + j];
-                        if (u == 0xFFFFu || ((er[u >> 5] >> (u & 31)) & 1u)) continue;
-                        const uint4 v = *reinterpret_cast<const uint4 *>(full + size_t(u) * p.S + ch + qd * 16);
-                        acc.x ^= v.x; acc.y ^= v.y; acc.z ^= v.z; acc.w ^= v.w;
-                    }
-                    *reinterpret_cast<uint4 *>(synd + size_t(r) * 64 + qd * 16) = acc;
+                    *reinterpret_cast<uint4 *>(synd + size_t(r) * 64 + qd * 16) = ge_rhs_quarter(p, cw, r, ch, qd);
                 }
                 __syncthreads();
                 for (int col = tid >> 2; col < e; col += kGeThreads / 4) {
@@ -237,7 +257,28 @@ struct GeWarpParams {
     unsigned int *count_out;
     unsigned int *work_ctr;              // next unclaimed list position
     int slot_words;                      // shared memory per warp, 32-bit words
+    // inactivation stage, split form: the pattern kernel records a plan per solvable codeword, the apply
+    // kernel replays it on the payload
+    uint32_t *plan;                      // [slots][plan_words] or nullptr (solve in place / pattern only)
+    unsigned int *plan_count;            // slots written
+    int plan_words;                      // stride, 32-bit words
+    int apply_slot_words;                // the apply kernel's shared memory per warp: what must fit to be planned
 };
+
+// plan of one codeword (32-bit words): header {cw, e, R, npeel, ninact, rank deficient, 0, 0}, then at fixed offsets
+// er[NW] | rowmap[m] varlist[m] pl_col[m] pl_row[m] (u16) | icol[64] (u16) | ipart[m] (u64) | nbr[m*VW] (u16)
+struct GePlanLayout {
+    int er, rowmap, varlist, pl_col, pl_row, icol, ipart, nbr, words;
+};
+__host__ __device__ inline GePlanLayout ge_plan_layout(int m, int NW, int VW)
+{
+    GePlanLayout L;
+    const int h = (m + 1) / 2;
+    L.er = 8; L.rowmap = L.er + NW; L.varlist = L.rowmap + h; L.pl_col = L.varlist + h; L.pl_row = L.pl_col + h;
+    L.icol = L.pl_row + h; L.ipart = (L.icol + 32 + 1) & ~1; L.nbr = L.ipart + 2 * m;
+    L.words = (L.nbr + (m * VW + 1) / 2 + 3) & ~3;
+    return L;
+}
 
 __host__ __device__ inline int ge_warp_fixed_words(int m, int NW)
 {   // er[NW+1] pref[NW+1] rowmap[m] varlist[m] pivrow[m] (u16 each), rounded to 16 bytes
@@ -262,7 +303,7 @@ __global__ void __launch_bounds__(512) hybrid_ge_warp_kernel(const GeWarpParams 
     uint16_t *pivrow = varlist + m + (m & 1);
     uint32_t *area = er + ge_warp_fixed_words(m, NW);
     const long long area_words = q.slot_words - ge_warp_fixed_words(m, NW);
-    const bool payload = p.full != nullptr;
+    const bool payload = p.synd != nullptr;
     const unsigned int count = *p.list_count;
 
     for (;;) {
@@ -355,32 +396,7 @@ __global__ void __launch_bounds__(512) hybrid_ge_warp_kernel(const GeWarpParams 
                     }
                 }
             }
-            if (payload) {   // syndromes: XOR of the KNOWN members, 8 rows x 4 quarters per pass
-                const uint8_t *full = p.full + size_t(cw) * p.n * p.S + ch;
-                const int qd = lane & 3;
-                for (int ri = lane >> 2; ri < R; ri += 8) {
-                    uint4 acc = make_uint4(0u, 0u, 0u, 0u);
-                    if (qd * 16 < cb) {
-                        const int r = rowmap[ri];
-                        for (int j0 = 0; j0 < RW; j0 += 8) {        // RW is a multiple of 8; eight gathers in flight
-                            const uint4 r4 = __ldg(reinterpret_cast<const uint4 *>(p.cidx + r * RW + j0));
-                            const uint32_t rr[4] = {r4.x, r4.y, r4.z, r4.w};
-                            uint4 v[8];
-                            bool use[8];
-#pragma unroll
-                            for (int t = 0; t < 8; t++) {
-                                const uint32_t u = (t & 1) ? (rr[t >> 1] >> 16) : (rr[t >> 1] & 0xFFFFu);
-                                use[t] = u != 0xFFFFu && !((er[(u == 0xFFFFu ? 0u : u) >> 5] >> (u & 31)) & 1u);
-                                v[t] = *reinterpret_cast<const uint4 *>(full + size_t(use[t] ? u : 0u) * p.S + qd * 16);
-                            }
-#pragma unroll
-                            for (int t = 0; t < 8; t++)
-                                if (use[t]) { acc.x ^= v[t].x; acc.y ^= v[t].y; acc.z ^= v[t].z; acc.w ^= v[t].w; }
-                        }
-                    }
-                    *reinterpret_cast<uint4 *>(bmat + size_t(ri) * kGeBPitch + qd * 4) = acc;
-                }
-            }
+            if (payload) ge_load_rhs(p, cw, rowmap, R, ch, cb / 16, bmat, kGeBPitch, lane);   // the executor's syndromes
             __syncwarp();
             // ---- 4. Gauss-Jordan, lane L owns rows L, L+32, ... -----------------------------------
             // (loads are issued in independent batches and the pivot row is held in registers: the
@@ -519,7 +535,8 @@ __global__ void __launch_bounds__(512) hybrid_inact_kernel(const GeWarpParams q)
     uint16_t *varlist = pl_row + mp;
     uint32_t *area = er + ge_inact_fixed_words(m, NW, MW);
     const long long area_words = q.slot_words - ge_inact_fixed_words(m, NW, MW);
-    const bool payload = p.full != nullptr;
+    const bool planning = q.plan != nullptr;                    // record the solution order, leave the payload to the apply kernel
+    const bool payload = p.synd != nullptr && !planning;
     const unsigned int count = *p.list_count;
     const int qd = lane & 3, hs = lane >> 2;                    // payload lanes: 16-byte quarter, hit slot
 
@@ -609,6 +626,7 @@ __global__ void __launch_bounds__(512) hybrid_inact_kernel(const GeWarpParams q)
             __syncwarp();
             lap(1);
             if (ge_inact_area_words(R, e, VW, payload) > area_words) { defer = true; break; }
+            if (planning && ge_inact_area_words(R, e, VW, true) > q.apply_slot_words - ge_inact_fixed_words(m, NW, MW)) { defer = true; break; }
             uint32_t *state = area;                                              // [R]
             unsigned long long *ipart = reinterpret_cast<unsigned long long *>(area + ((R + 1) & ~1));   // [R]
             uint16_t *nbr = reinterpret_cast<uint16_t *>(area + ((3 * R + 3) & ~3));   // [e][VW] rows of each unknown
@@ -621,37 +639,7 @@ __global__ void __launch_bounds__(512) hybrid_inact_kernel(const GeWarpParams q)
                 const uint32_t chk = __ldg(p.vadj + size_t(varlist[i / VW]) * VW + (i % VW));
                 nbr[i] = chk == 0xFFFFu ? uint16_t(0xFFFFu) : inv_rowmap[chk];
             }
-            if (payload) {   // syndromes: XOR of the KNOWN members, 8 rows x 4 quarters per pass, 16 gathers in flight
-                const uint8_t *full = p.full + size_t(cw) * p.n * p.S + ch;
-                for (int ri = hs; ri < R; ri += 8) {
-                    uint4 acc = make_uint4(0u, 0u, 0u, 0u);
-                    if (qd * 16 < cb) {
-                        const int r = rowmap[ri];
-                        for (int j0 = 0; j0 < RW; j0 += 16) {
-                            uint4 v[16];
-                            bool use[16];
-#pragma unroll
-                            for (int h = 0; h < 2; h++) {
-                                const bool in = j0 + 8 * h < RW;      // RW is a multiple of 8
-                                const uint4 r4 = in ? __ldg(reinterpret_cast<const uint4 *>(p.cidx + r * RW + j0 + 8 * h))
-                                                    : make_uint4(FULL, FULL, FULL, FULL);
-                                const uint32_t rr[4] = {r4.x, r4.y, r4.z, r4.w};
-#pragma unroll
-                                for (int t = 0; t < 8; t++) {
-                                    const uint32_t u = (t & 1) ? (rr[t >> 1] >> 16) : (rr[t >> 1] & 0xFFFFu);
-                                    const uint32_t us = u == 0xFFFFu ? 0u : u;
-                                    use[8 * h + t] = u != 0xFFFFu && !((er[us >> 5] >> (us & 31)) & 1u);
-                                    v[8 * h + t] = *reinterpret_cast<const uint4 *>(full + size_t(use[8 * h + t] ? u : 0u) * p.S + qd * 16);
-                                }
-                            }
-#pragma unroll
-                            for (int t = 0; t < 16; t++)
-                                if (use[t]) { acc.x ^= v[t].x; acc.y ^= v[t].y; acc.z ^= v[t].z; acc.w ^= v[t].w; }
-                        }
-                    }
-                    *reinterpret_cast<uint4 *>(bmat + size_t(ri) * 16 + qd * 4) = acc;
-                }
-            }
+            if (payload) ge_load_rhs(p, cw, rowmap, R, ch, cb / 16, bmat, 16, lane);          // the executor's syndromes
             __syncwarp();
 
             lap(2);
@@ -752,6 +740,25 @@ __global__ void __launch_bounds__(512) hybrid_inact_kernel(const GeWarpParams q)
             }
             lap(3);
             if (!ok || defer) break;
+            unsigned int plan_slot = 0;
+            if (planning) {   // snapshot for the apply kernel: ipart as it is BEFORE the dense solve
+                if (lane == 0) plan_slot = atomicAdd(q.plan_count, 1u);
+                plan_slot = __shfl_sync(FULL, plan_slot, 0);
+                const GePlanLayout L = ge_plan_layout(m, NW, VW);
+                uint32_t *pw = q.plan + size_t(plan_slot) * q.plan_words;
+                if (lane == 0) { pw[0] = uint32_t(cw); pw[1] = uint32_t(e); pw[2] = uint32_t(R); pw[3] = uint32_t(npeel); pw[4] = uint32_t(ninact); pw[5] = 0u; }
+                for (int i = lane; i < NW; i += 32) pw[L.er + i] = er[i];
+                const uint32_t *s_rowmap = reinterpret_cast<const uint32_t *>(rowmap), *s_var = reinterpret_cast<const uint32_t *>(varlist);
+                const uint32_t *s_pc = reinterpret_cast<const uint32_t *>(pl_col), *s_pr = reinterpret_cast<const uint32_t *>(pl_row);
+                for (int i = lane; i < (R + 1) / 2; i += 32) pw[L.rowmap + i] = s_rowmap[i];
+                for (int i = lane; i < (e + 1) / 2; i += 32) pw[L.varlist + i] = s_var[i];
+                for (int i = lane; i < (npeel + 1) / 2; i += 32) { pw[L.pl_col + i] = s_pc[i]; pw[L.pl_row + i] = s_pr[i]; }
+                pw[L.icol + lane] = reinterpret_cast<const uint32_t *>(icol)[lane];
+                const uint32_t *s_ip = reinterpret_cast<const uint32_t *>(ipart);
+                for (int i = lane; i < 2 * R; i += 32) pw[L.ipart + i] = s_ip[i];
+                const uint32_t *s_nb = reinterpret_cast<const uint32_t *>(nbr);
+                for (int i = lane; i < (e * VW + 1) / 2; i += 32) pw[L.nbr + i] = s_nb[i];
+            }
 
             // ---- phase 2: the unused rows are equations in the inactive unknowns only ----------------------
             for (int c = 0; c < ninact; c++) {
@@ -782,6 +789,7 @@ __global__ void __launch_bounds__(512) hybrid_inact_kernel(const GeWarpParams q)
                 __syncwarp();
             }
             lap(4);
+            if (planning && !ok && lane == 0) q.plan[size_t(plan_slot) * q.plan_words + 5] = 1u;   // rank deficient: nothing to apply
             if (!ok) break;
 
             // ---- phase 3: read the unknowns off their pivot rows ----------------------------------------------
@@ -825,14 +833,166 @@ __global__ void __launch_bounds__(512) hybrid_inact_kernel(const GeWarpParams q)
     }
 }
 
+
+// Payload part of the inactivation stage: replays a recorded plan.  One warp per codeword; the pattern
+// kernel above (which needs 3 words per row instead of 19) found the pivots at full occupancy.
+__global__ void __launch_bounds__(512) hybrid_apply_kernel(const GeWarpParams q)
+{
+    extern __shared__ __align__(16) uint32_t gw_smem[];
+    constexpr unsigned FULL = 0xFFFFFFFFu;
+    constexpr uint32_t USED = 0x80000000u, TAKEN = 0x40000000u;
+    const GeParams &p = q.g;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int m = p.m, NW = p.NW, MW = p.MW, VW = p.VW;
+    uint32_t *er = gw_smem + size_t(warp) * q.slot_words;     // same fixed layout as the pattern kernel
+    uint32_t *pref = er + NW + 1;
+    uint32_t *d1 = pref + NW + 1;
+    uint32_t *act = d1 + MW;
+    uint16_t *icol = reinterpret_cast<uint16_t *>(act + MW);
+    uint16_t *ipiv = icol + kInactMax;
+    const int mp = m + (m & 1);
+    uint16_t *inv_rowmap = ipiv + kInactMax;
+    uint16_t *rowmap = inv_rowmap + mp;
+    uint16_t *pl_col = rowmap + mp;
+    uint16_t *pl_row = pl_col + mp;
+    uint16_t *varlist = pl_row + mp;
+    uint32_t *area = er + ge_inact_fixed_words(m, NW, MW);
+    const GePlanLayout L = ge_plan_layout(m, NW, VW);
+    const unsigned int count = *q.plan_count;
+    const int qd = lane & 3, hs = lane >> 2;
+
+    for (;;) {
+        unsigned int li = 0;
+        if (lane == 0) li = atomicAdd(q.work_ctr, 1u);
+        li = __shfl_sync(FULL, li, 0);
+        if (li >= count) break;
+        const uint32_t *pw = q.plan + size_t(li) * q.plan_words;
+        long long tmark = p.phase_cycles ? clock64() : 0;
+        auto lap = [&](int ph) {
+            if (p.phase_cycles) {
+                const long long t = clock64();
+                if (lane == 0) atomicAdd(&p.phase_cycles[ph], (unsigned long long)(t - tmark));
+                tmark = t;
+            }
+        };
+        if (pw[5] != 0u) continue;                               // rank deficient: the peeling result stays
+        const long long cw = pw[0];
+        const int e = int(pw[1]), R = int(pw[2]), npeel = int(pw[3]), ninact = int(pw[4]);
+        uint32_t *state = area;                                              // [R] flags only
+        unsigned long long *ipart = reinterpret_cast<unsigned long long *>(area + ((R + 1) & ~1));
+        uint16_t *nbr = reinterpret_cast<uint16_t *>(area + ((3 * R + 3) & ~3));
+        uint32_t *bmat = area + ((3 * R + 3) & ~3) + (((e * VW + 1) / 2 + 3) & ~3);
+        // ---- the plan -> shared memory ----------------------------------------------------------
+        for (int i = lane; i < NW; i += 32) er[i] = pw[L.er + i];
+        for (int i = lane; i < (R + 1) / 2; i += 32) reinterpret_cast<uint32_t *>(rowmap)[i] = pw[L.rowmap + i];
+        for (int i = lane; i < (e + 1) / 2; i += 32) reinterpret_cast<uint32_t *>(varlist)[i] = pw[L.varlist + i];
+        for (int i = lane; i < (npeel + 1) / 2; i += 32) {
+            reinterpret_cast<uint32_t *>(pl_col)[i] = pw[L.pl_col + i];
+            reinterpret_cast<uint32_t *>(pl_row)[i] = pw[L.pl_row + i];
+        }
+        reinterpret_cast<uint32_t *>(icol)[lane] = pw[L.icol + lane];
+        for (int i = lane; i < (e * VW + 1) / 2; i += 32) reinterpret_cast<uint32_t *>(nbr)[i] = pw[L.nbr + i];
+        __syncwarp();
+        lap(0);
+
+        for (int ch = 0; ch < p.S; ch += 64) {
+            const int cb = min(64, p.S - ch);
+            const int nq = cb / 16;
+            for (int i = lane; i < 2 * R; i += 32) reinterpret_cast<uint32_t *>(ipart)[i] = pw[L.ipart + i];
+            for (int i = lane; i < R; i += 32) state[i] = 0u;
+            __syncwarp();
+            for (int i = lane; i < npeel; i += 32) state[pl_row[i]] = USED;
+            ge_load_rhs(p, cw, rowmap, R, ch, nq, bmat, 16, lane);     // right-hand sides: the executor's syndromes
+            __syncwarp();
+            lap(1);
+            // ---- phase 1 replay: b[row] ^= b[pivot] for the other rows of each peeled unknown, in order ----
+            for (int i0 = 0; i0 < npeel; i0 += 32) {
+                const int mycol = (i0 + lane < npeel) ? pl_col[i0 + lane] : 0;
+                const int myrow = (i0 + lane < npeel) ? pl_row[i0 + lane] : 0;
+                const int cnt = min(32, npeel - i0);
+                for (int t = 0; t < cnt; t++) {
+                    const int col = __shfl_sync(FULL, mycol, t), ri = __shfl_sync(FULL, myrow, t);
+                    uint32_t rj = 0xFFFFu;
+                    if (lane < VW) rj = nbr[col * VW + lane];
+                    const unsigned hb = __ballot_sync(FULL, rj != 0xFFFFu && int(rj) != ri);
+                    if (!hb) continue;
+                    const uint4 pb = *reinterpret_cast<const uint4 *>(bmat + size_t(ri) * 16 + qd * 4);
+                    const int nh = __popc(hb);
+                    for (int h0 = 0; h0 < nh; h0 += 8) {
+                        const int src = __fns(hb, 0, h0 + hs + 1);       // lane holding the (h0+hs)-th hit, -1 if none
+                        const int r2 = __shfl_sync(FULL, int(rj), src < 0 ? 0 : src);
+                        if (src >= 0 && src < 32 && qd < nq) {
+                            uint4 *br = reinterpret_cast<uint4 *>(bmat + size_t(r2) * 16 + qd * 4);
+                            uint4 a4 = *br;
+                            a4.x ^= pb.x; a4.y ^= pb.y; a4.z ^= pb.z; a4.w ^= pb.w;
+                            *br = a4;
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+            lap(2);
+            // ---- phase 2: dense solve on [ipart | b] of the unused rows (the plan is known to have full rank) ----
+            for (int c = 0; c < ninact; c++) {
+                unsigned best = 0xFFFFFFFFu;
+                for (int r0 = lane; r0 < R; r0 += 32)
+                    if (!(state[r0] & (USED | TAKEN)) && ((ipart[r0] >> c) & 1u)) { best = uint32_t(r0); break; }
+                best = __reduce_min_sync(FULL, best);
+                if (best == 0xFFFFFFFFu) break;                           // (cannot happen: the pattern kernel found the pivots)
+                const int pr = int(best);
+                const unsigned long long pI = ipart[pr];
+                uint32_t pb = 0u;
+                if (lane < 16) pb = bmat[size_t(pr) * 16 + lane];
+                __syncwarp();
+                if (lane == 0) { state[pr] |= TAKEN; ipiv[c] = uint16_t(pr); }
+                for (int r0 = 0; r0 < R; r0 += 32) {
+                    const int r2 = r0 + lane;
+                    const bool hit = r2 < R && r2 != pr && !(state[r2] & USED) && ((ipart[r2] >> c) & 1u);
+                    if (hit) ipart[r2] ^= pI;
+                    unsigned hb = __ballot_sync(FULL, hit);
+                    while (hb) {
+                        const int hl = __ffs(hb) - 1;
+                        hb &= hb - 1u;
+                        if (lane < 16) bmat[size_t(r0 + hl) * 16 + lane] ^= pb;
+                    }
+                }
+                __syncwarp();
+            }
+            lap(3);
+            // ---- phase 3: read the unknowns off their pivot rows -----------------------------------------
+            uint8_t *out = p.out + size_t(cw) * p.k * p.S + ch;
+            for (int i = hs; i < npeel + ninact; i += 8) {
+                const bool pe = i < npeel;
+                const int u = varlist[pe ? pl_col[i] : icol[i - npeel]];
+                const int r = pe ? pl_row[i] : ipiv[i - npeel];
+                if (u >= p.k || qd >= nq) continue;                       // only systematic symbols are output
+                uint4 acc = *reinterpret_cast<const uint4 *>(bmat + size_t(r) * 16 + qd * 4);
+                unsigned long long bits = pe ? ipart[r] : 0ull;
+                while (bits) {
+                    const int c = __ffsll((long long)bits) - 1;
+                    bits &= bits - 1ull;
+                    const uint4 v = *reinterpret_cast<const uint4 *>(bmat + size_t(ipiv[c]) * 16 + qd * 4);
+                    acc.x ^= v.x; acc.y ^= v.y; acc.z ^= v.z; acc.w ^= v.w;
+                }
+                *reinterpret_cast<uint4 *>(out + size_t(u) * p.S + qd * 16) = acc;
+            }
+            __syncwarp();
+            lap(4);
+        }
+        if (p.phase_cycles && lane == 0) atomicAdd(&p.phase_cycles[6], 1ull);
+    }
+}
+
 // ---- host side -------------------------------------------------------------------------------
 struct HybridScratch {
-    uint8_t *d_full = nullptr;          // [max_batch][n][S]
+    uint8_t *d_synd = nullptr;          // [max_batch][m][S] check syndromes written by the executor
     unsigned int *d_list = nullptr;     // [max_batch] stalled codewords, written by the peel kernel
     unsigned int *d_list2 = nullptr, *d_list3 = nullptr, *d_list4 = nullptr;   // deferred by warp stages 0 / 1 / 2
-    unsigned int *d_count = nullptr;    // [8]: list counts [0..3], work counters [4..6]
+    unsigned int *d_count = nullptr;    // [16]: list counts [0..3], work counters [4..6], plan counts [8..9], apply work counters [10..11]
     // warp stages: [0] inactivation, typical slots; [1] inactivation, worst-case slots; [2] per-warp Gauss-Jordan
     int wpc[3] = {0, 0, 0}, slot_words[3] = {0, 0, 0};
+    uint32_t *d_plan = nullptr;          // [max_batch][plan_words] recorded solutions of the inactivation stage
+    int plan_words = 0;
     int wpc_pat = 0, slot_words_pat = 0;                     // stage 0 without payload (error-rate runs): smaller slots
     uint32_t *d_gmat = nullptr;         // per-CTA matrices when they do not fit in shared memory
     int grid = 0, smem = 0, RSW = 0;
@@ -841,7 +1001,7 @@ struct HybridScratch {
 
 inline void hybrid_free(HybridScratch &h)
 {
-    cudaFree(h.d_full); cudaFree(h.d_list); cudaFree(h.d_list2); cudaFree(h.d_list3); cudaFree(h.d_list4); cudaFree(h.d_count); cudaFree(h.d_gmat);
+    cudaFree(h.d_synd); cudaFree(h.d_list); cudaFree(h.d_list2); cudaFree(h.d_list3); cudaFree(h.d_list4); cudaFree(h.d_plan); cudaFree(h.d_count); cudaFree(h.d_gmat);
     h = HybridScratch();
 }
 
@@ -855,12 +1015,12 @@ inline int hybrid_prepare(HybridScratch &h, const HostCode &code, int S, int NW,
         return e == cudaErrorMemoryAllocation ? LDPC_ERR_NOMEM : LDPC_ERR_CUDA;
     };
     cudaError_t e;
-    if ((e = cudaMalloc(&h.d_full, size_t(max_batch) * code.n * S)) != cudaSuccess) return bad("hybrid: full-codeword scratch", e);
+    if ((e = cudaMalloc(&h.d_synd, size_t(max_batch) * code.m * S)) != cudaSuccess) return bad("hybrid: syndrome scratch", e);
     if ((e = cudaMalloc(&h.d_list, size_t(max_batch) * 4)) != cudaSuccess) return bad("hybrid: list", e);
     if ((e = cudaMalloc(&h.d_list2, size_t(max_batch) * 4)) != cudaSuccess) return bad("hybrid: list", e);
     if ((e = cudaMalloc(&h.d_list3, size_t(max_batch) * 4)) != cudaSuccess) return bad("hybrid: list", e);
     if ((e = cudaMalloc(&h.d_list4, size_t(max_batch) * 4)) != cudaSuccess) return bad("hybrid: list", e);
-    if ((e = cudaMalloc(&h.d_count, 8 * 4)) != cudaSuccess) return bad("hybrid: count", e);
+    if ((e = cudaMalloc(&h.d_count, 16 * 4)) != cudaSuccess) return bad("hybrid: count", e);
     {   // warp stages: [0] inactivation decoding, slots for a typical stopping set (2/3 of the checks involved);
         //              [1] the same with worst-case slots, for what [0] defers for size;
         //              [2] plain Gauss-Jordan per warp, worst-case slots: more than kInactMax inactivations
@@ -888,6 +1048,11 @@ inline int hybrid_prepare(HybridScratch &h, const HostCode &code, int S, int NW,
             return bad("hybrid: cudaFuncSetAttribute", e);
         if ((e = cudaFuncSetAttribute(hybrid_inact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin - 1024)) != cudaSuccess)
             return bad("hybrid: cudaFuncSetAttribute", e);
+        if ((e = cudaFuncSetAttribute(hybrid_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin - 1024)) != cudaSuccess)
+            return bad("hybrid: cudaFuncSetAttribute", e);
+        h.plan_words = ge_plan_layout(code.m, NW, code.VW).words;
+        if (h.wpc[0] > 0 && h.wpc_pat > 0)
+            if ((e = cudaMalloc(&h.d_plan, size_t(max_batch) * h.plan_words * 4)) != cudaSuccess) return bad("hybrid: plan buffer", e);
     }
     h.RSW = 2 * MW + 1;
     const size_t base = size_t(code.m) * 64 + ge_small_bytes(code.m, NW) + 16;

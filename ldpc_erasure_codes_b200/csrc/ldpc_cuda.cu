@@ -57,6 +57,8 @@ static int allow_max_smem(const void *func, int smem_optin)
 
 // LDPC_CUDA_GE_STAGES: bit 0 = inactivation stage, bit 1 = per-warp elimination stage (default 3); the
 // CTA-per-codeword kernel always runs last on what is left.  Tests use it to compare the solvers.
+// LDPC_CUDA_GE_SPLIT=0: the inactivation stage solves pattern and payload in one kernel (tests compare both forms)
+static bool ge_split() { const char *e = getenv("LDPC_CUDA_GE_SPLIT"); return !(e && *e == '0'); }
 static int ge_stage_mask() { const char *e = getenv("LDPC_CUDA_GE_STAGES"); return e && *e ? atoi(e) : 3; }
 
 // LDPC_CUDA_DEBUG_SYNC=1: synchronise after every launch so that a faulting kernel is named
@@ -197,7 +199,8 @@ static int choose_geom(const ldpc_ctx *c, bool dynamic_sched, ExecGeom *g)
     const int n = c->code.n, S = c->S;
     const int cidx_bytes = c->code.m * c->code.RW * 2;
     const int blob = sched_blob_max_bytes(c->code.m);
-    const int fixed = cidx_bytes + 128 + 128 + 64 + 128 + 128;
+    const int mask_bytes = dynamic_sched ? kExecMaxGroups * ((c->NW + 3) & ~3) * 4 : 0;   // hybrid mode: one mask per slot
+    const int fixed = cidx_bytes + 128 + 128 + 64 + 128 + 128 + mask_bytes;
     ExecGeom best;
     for (int W = 64; W >= 16; W >>= 1) {         // instantiated slice widths; S is a multiple of 16, so 16 always divides
         if (W > S || S % W) continue;
@@ -211,7 +214,7 @@ static int choose_geom(const ldpc_ctx *c, bool dynamic_sched, ExecGeom *g)
         if (nslot < 1) continue;
         ExecGeom cand;
         cand.W = W; cand.nslot = nslot; cand.slot_bytes = slot; cand.sched_area = blob;
-        cand.smem_bytes = nslot * slot + (dynamic_sched ? nslot : 1) * blob + cidx_bytes + 128 + 128 + 64 + 128;
+        cand.smem_bytes = nslot * slot + (dynamic_sched ? nslot : 1) * blob + cidx_bytes + 128 + 128 + 64 + 128 + mask_bytes;
         if (!best.W || (best.nslot < 3 && cand.nslot > best.nslot)) best = cand;
         if (best.nslot >= 3) break;
     }
@@ -342,8 +345,8 @@ extern "C" int ldpc_ctx_create(ldpc_ctx **out, const char *h_mat_path, int code_
     CTX_TRY(cudaMalloc(&c->d_work_ctr, sizeof(unsigned int)));
     if (const char *e = getenv("LDPC_CUDA_PHASE_TIMING")) {
         if (*e && *e != '0') {
-            CTX_TRY(cudaMalloc(&c->d_phase, 16 * sizeof(unsigned long long)));
-            CTX_TRY(cudaMemset(c->d_phase, 0, 16 * sizeof(unsigned long long)));
+            CTX_TRY(cudaMalloc(&c->d_phase, 24 * sizeof(unsigned long long)));
+            CTX_TRY(cudaMemset(c->d_phase, 0, 24 * sizeof(unsigned long long)));
         }
     }
 #undef CTX_TRY
@@ -415,7 +418,7 @@ extern "C" int ldpc_ctx_set_exec_geometry(ldpc_ctx *c, int slice_bytes, int slot
 // ------------------------------------------------------------------------------------------
 // executor launch
 // ------------------------------------------------------------------------------------------
-typedef void (*ExecKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const ExecParams);
+typedef void (*ExecKernel)(const CUtensorMap, const CUtensorMap, const ExecParams);
 
 // instantiated member counts: 7 / 14 are the committed codes' maximum row weights
 static ExecKernel pick_exec(int W, int max_row_weight, int *rwm_out)
@@ -443,18 +446,16 @@ static ExecKernel pick_exec(int W, int max_row_weight, int *rwm_out)
 
 static int launch_exec(ldpc_ctx *c, const ExecGeom &g, const void *d_in, int rows_in, void *d_out, int rows_out,
                        const uint8_t *sched, const uint32_t *sched_len, int sched_stride, long long B,
-                       cudaStream_t st, void *d_full = nullptr)
+                       cudaStream_t st, uint8_t *d_synd = nullptr, const uint32_t *d_mask = nullptr)
 {
     if (B <= 0) return LDPC_OK;
-    CUtensorMap in_map, out_map, full_map;
+    CUtensorMap in_map, out_map;
     int rc = make_map(&in_map, d_in, c->S, rows_in, B, g.W, true);
     if (rc) return rc;
     rc = make_map(&out_map, d_out, c->S, rows_out, B, g.W, false);
     if (rc) return rc;
-    rc = make_map(&full_map, d_full ? d_full : d_in, c->S, rows_in, B, g.W, false);
-    if (rc) return rc;
     ExecParams p;
-    p.store_full = d_full ? 1 : 0;
+    p.synd = d_synd; p.mask = d_mask; p.NW = c->NW;
     p.cidx = c->d_cidx; p.sched = sched; p.sched_len = sched_len; p.B = B; p.sched_stride = sched_stride;
     p.sched_max = g.sched_area; p.m = c->code.m; p.RW = c->code.RW; p.rows_in = rows_in; p.rows_out = rows_out;
     p.nbox_in = (rows_in + kBoxRows - 1) / kBoxRows; p.nbox_out = (rows_out + kBoxRows - 1) / kBoxRows;
@@ -468,7 +469,7 @@ static int launch_exec(ldpc_ctx *c, const ExecGeom &g, const void *d_in, int row
     const int grid = int(std::min<long long>(c->num_sms, B));
     {
         ProfScope ps(c, sched_stride ? LDPC_K_EXEC_DECODE : LDPC_K_EXEC_ENCODE, st);
-        k<<<grid, g.nslot * kExecWarpsPerGroup * 32, g.smem_bytes, st>>>(in_map, out_map, full_map, p);
+        k<<<grid, g.nslot * kExecWarpsPerGroup * 32, g.smem_bytes, st>>>(in_map, out_map, p);
     }
     CUDA_TRY(cudaGetLastError());
     return debug_sync(sched_stride ? "payload_exec_kernel(decode)" : "payload_exec_kernel(encode)", st);
@@ -592,7 +593,7 @@ static int decode_chunk(ldpc_ctx *c, const uint8_t *d_cw, const uint32_t *d_mask
     if (mode == LDPC_MODE_HYBRID) {
         int rch = hybrid_prepare(c->hyb, c->code, c->S, c->NW, c->MW, c->num_sms, c->smem_optin, c->max_batch, g_err);
         if (rch) return rch;
-        CUDA_TRY(cudaMemsetAsync(c->hyb.d_count, 0, 8 * 4, st));
+        CUDA_TRY(cudaMemsetAsync(c->hyb.d_count, 0, 16 * 4, st));
         pp.ge_list = c->hyb.d_list; pp.ge_count = c->hyb.d_count;
     }
     const int grid = int(std::min<long long>(c->num_sms, (B + c->peel_groups - 1) / c->peel_groups));
@@ -606,13 +607,13 @@ static int decode_chunk(ldpc_ctx *c, const uint8_t *d_cw, const uint32_t *d_mask
     const bool pattern_only = d_cw == nullptr;   // error-rate run: no payload
     if (!pattern_only) {
         int rc = launch_exec(c, c->dec, d_cw, c->code.n, d_out, c->code.k, sched, sched_len, c->sched_stride, B, st,
-                             mode == LDPC_MODE_HYBRID ? c->hyb.d_full : nullptr);
+                             mode == LDPC_MODE_HYBRID ? c->hyb.d_synd : nullptr, d_mask);
         if (rc) return rc;
     }
     if (mode == LDPC_MODE_HYBRID) {
         GeParams gp;
         gp.mask = d_mask; gp.sched = sched; gp.list = c->hyb.d_list; gp.list_count = c->hyb.d_count;
-        gp.full = pattern_only ? nullptr : c->hyb.d_full; gp.out = d_out; gp.fail = pp.fail; gp.stats = c->d_stats; gp.cidx = c->d_cidx;
+        gp.synd = pattern_only ? nullptr : c->hyb.d_synd; gp.out = d_out; gp.fail = pp.fail; gp.stats = c->d_stats; gp.cidx = c->d_cidx;
         gp.vadj = c->d_vadj; gp.VW = c->code.VW; gp.phase_cycles = c->d_phase ? c->d_phase + 8 : nullptr; gp.gmat = c->hyb.d_gmat; gp.n = c->code.n; gp.k = c->code.k; gp.m = c->code.m; gp.RW = c->code.RW; gp.NW = c->NW;
         gp.MW = c->MW; gp.S = c->S; gp.stride = c->sched_stride; gp.RSW = c->hyb.RSW;
         // warp-per-codeword stages first (inactivation decoding with typical, then worst-case slots; then plain
@@ -626,12 +627,28 @@ static int decode_chunk(ldpc_ctx *c, const uint8_t *d_cw, const uint32_t *d_mask
             wp.g = gp; wp.g.list = lists[li]; wp.g.list_count = c->hyb.d_count + li;
             wp.list_out = const_cast<unsigned int *>(lists[li + 1]); wp.count_out = c->hyb.d_count + li + 1;
             int wpc = c->hyb.wpc[sg], slot = c->hyb.slot_words[sg];
+            wp.plan = nullptr; wp.plan_count = nullptr; wp.plan_words = 0; wp.apply_slot_words = 0;
+            const bool split = sg < 2 && !pattern_only && c->hyb.d_plan && c->hyb.wpc_pat > 0 && ge_split();
             if (sg == 0 && pattern_only && c->hyb.wpc_pat > 0) { wpc = c->hyb.wpc_pat; slot = c->hyb.slot_words_pat; }
+            if (split) {   // pattern part at full occupancy, recording plans; the payload replay follows
+                wp.plan = c->hyb.d_plan; wp.plan_count = c->hyb.d_count + 8 + sg; wp.plan_words = c->hyb.plan_words;
+                wp.apply_slot_words = c->hyb.slot_words[sg];
+                wpc = c->hyb.wpc_pat; slot = c->hyb.slot_words_pat;
+            }
             wp.work_ctr = c->hyb.d_count + 4 + sg; wp.slot_words = slot;
             const size_t smem = size_t(wpc) * slot * 4;
-            ProfScope ps(c, sg < 2 ? LDPC_K_HYBRID : LDPC_K_HYBRID_WARP, st);
-            if (sg < 2) hybrid_inact_kernel<<<c->num_sms, 32 * wpc, smem, st>>>(wp);
-            else hybrid_ge_warp_kernel<<<c->num_sms, 32 * wpc, smem, st>>>(wp);
+            {
+                ProfScope ps(c, sg < 2 ? LDPC_K_HYBRID : LDPC_K_HYBRID_WARP, st);
+                if (sg < 2) hybrid_inact_kernel<<<c->num_sms, 32 * wpc, smem, st>>>(wp);
+                else hybrid_ge_warp_kernel<<<c->num_sms, 32 * wpc, smem, st>>>(wp);
+            }
+            if (split) {
+                GeWarpParams ap = wp;
+                if (ap.g.phase_cycles) ap.g.phase_cycles += 8;
+                ap.work_ctr = c->hyb.d_count + 10 + sg; ap.slot_words = c->hyb.slot_words[sg];
+                ProfScope ps(c, LDPC_K_HYBRID_APPLY, st);
+                hybrid_apply_kernel<<<c->num_sms, 32 * c->hyb.wpc[sg], size_t(c->hyb.wpc[sg]) * c->hyb.slot_words[sg] * 4, st>>>(ap);
+            }
             li++;
         }
         gp.list = lists[li]; gp.list_count = c->hyb.d_count + li;
@@ -738,7 +755,8 @@ extern "C" int ldpc_profile_read(ldpc_ctx *c, ldpc_profile *out, int reset)
     if (c->d_phase) {
         CUDA_TRY(cudaMemcpy(out->exec_phase_cycles, c->d_phase, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
         CUDA_TRY(cudaMemcpy(out->ge_phase_cycles, c->d_phase + 8, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-        if (reset) CUDA_TRY(cudaMemset(c->d_phase, 0, 16 * sizeof(unsigned long long)));
+        CUDA_TRY(cudaMemcpy(out->apply_phase_cycles, c->d_phase + 16, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        if (reset) CUDA_TRY(cudaMemset(c->d_phase, 0, 24 * sizeof(unsigned long long)));
     }
     if (reset) {
         for (auto &r : c->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }

@@ -45,7 +45,9 @@ struct ExecParams {
     int slices;                 // S / W
     int nslot;                  // = number of warp groups
     int slot_bytes;             // shared bytes per slot
-    int store_full;             // hybrid mode: units whose codeword still has erasures also store all rows_in rows to full_map
+    uint8_t *synd;              // hybrid mode: [B][m][S] check syndromes of the codewords that still have erasures, or nullptr
+    const uint32_t *mask;       // hybrid mode: [B][NW] erasure masks (erased rows are zeroed in the slot before the XOR phase)
+    int NW;
     unsigned long long *phase_cycles;  // tuning aid (nullptr = off): [0] claim+issue, [1] load wait, [2] XOR, [3] store, [4] units
 };
 
@@ -68,7 +70,7 @@ __device__ __forceinline__ void sts128(uint32_t addr, const uint4 v)
 template <int W, int RWM>  // W = slice bytes; RWM = members gathered per check (>= max row weight)
 __global__ void __launch_bounds__(kExecMaxGroups *kExecWarpsPerGroup * 32, 1)
 payload_exec_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap out_map,
-                    const __grid_constant__ CUtensorMap full_map, const ExecParams p)
+                    const ExecParams p)
 {
     constexpr int RWQ = (RWM + 7) / 8;                // uint4 chunks of a padded check row
     constexpr int LPG = W / 16;                       // lanes per entry
@@ -83,6 +85,7 @@ payload_exec_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
     uint64_t *full = reinterpret_cast<uint64_t *>(cidx_s + size_t(p.m) * (RWQ * 8));   // [nslot]
     uint8_t *zrow = reinterpret_cast<uint8_t *>(full + 8);   // 64 zero bytes: what a skipped member reads
     int *mailbox = reinterpret_cast<int *>(zrow + 64);       // [g] unit of group g, [8] next unit, [16 + g] level hand-off
+    uint32_t *msk_s = reinterpret_cast<uint32_t *>(mailbox + 32) + (threadIdx.x / GT) * ((p.NW + 3) & ~3);   // hybrid mode: the unit's mask
 
     const int g = threadIdx.x / GT;          // group = slot
     const int tg = threadIdx.x % GT;         // thread in group
@@ -160,9 +163,22 @@ payload_exec_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
         const int j = mailbox[g];
         if (j >= n_units) break;
         lap(0);
+        if (p.synd) {   // hybrid mode: fetch the codeword's erasure mask while the slot loads
+            const long long b = blockIdx.x + (long long)(j / p.slices) * gridDim.x;
+            for (int w = tg; w < p.NW; w += GT) msk_s[w] = p.mask[b * p.NW + w];
+        }
         mbar_wait(&full[g], phase);
         phase ^= 1u;
         lap(1);
+        if (p.synd) {
+            // Symbols that stay unknown must read as zero when the syndromes are formed below.  Erased symbols
+            // are zero on input by contract; zeroing them here makes the decoder independent of that.
+            named_bar_sync(bar_id, GT);
+            const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+            for (int u = tg / LPG; u < p.rows_in; u += NGROUPS)
+                if ((msk_s[u >> 5] >> (u & 31)) & 1u) sts128(base_a + u * W, z4);
+            named_bar_sync(bar_id, GT);
+        }
 
         // ---- XOR the schedule into the slot -----------------------------------------------
         // The level walk is a chain of shared-memory round trips (a level's gathers cannot start
@@ -290,14 +306,39 @@ payload_exec_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
         fence_proxy_async_smem();
         named_bar_sync(bar_id, GT);
         lap(2);
+        if (p.synd) {
+            // Hybrid mode, codeword still has erasures: the elimination stage needs, per check, the XOR of the
+            // members known NOW.  They are all in the slot, so the syndromes are formed here -- one level, no
+            // chain -- instead of being gathered from HBM later.  Every member is XORed in: the symbols that
+            // are still unknown were zeroed above.
+            if (reinterpret_cast<const uint32_t *>(blob)[2] != 0u) {
+                const long long b = blockIdx.x + (long long)(j / p.slices) * gridDim.x;
+                uint8_t *dst = p.synd + (size_t(b) * p.m) * (size_t(p.slices) * W) + size_t(j % p.slices) * W + (tg % LPG) * 16;
+                for (int r = tg / LPG; r < p.m; r += NGROUPS) {
+                    const uint4 *row = reinterpret_cast<const uint4 *>(cidx_s + size_t(r) * (RWQ * 8));
+                    uint32_t rr[RWQ * 4];
+#pragma unroll
+                    for (int qq = 0; qq < RWQ; qq++) {
+                        const uint4 r4 = row[qq];
+                        rr[qq * 4 + 0] = r4.x; rr[qq * 4 + 1] = r4.y; rr[qq * 4 + 2] = r4.z; rr[qq * 4 + 3] = r4.w;
+                    }
+                    uint4 acc = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+                    for (int t = 0; t < RWM; t++) {
+                        const uint32_t u = (t & 1) ? (rr[t >> 1] >> 16) : (rr[t >> 1] & 0xFFFFu);
+                        const uint4 v = lds128(u == 0xFFFFu ? zero_a : base_a + u * W);
+                        acc.x ^= v.x; acc.y ^= v.y; acc.z ^= v.z; acc.w ^= v.w;
+                    }
+                    *reinterpret_cast<uint4 *>(dst + size_t(r) * (size_t(p.slices) * W)) = acc;
+                }
+            }
+            named_bar_sync(bar_id, GT);   // the slot is recycled by the leader below: every gather must be done
+        }
         if (leader) {
             const long long b = blockIdx.x + (long long)(j / p.slices) * gridDim.x;
             const int sl = j % p.slices;
             for (int q = 0; q < p.nbox_out; q++)
                 tma_store_3d(&out_map, slot + size_t(q) * kBoxRows * W, sl * W, q * kBoxRows, int(b));
-            if (p.store_full && reinterpret_cast<const uint32_t *>(blob)[2] != 0u)   // erasures left: the elimination stage
-                for (int q = 0; q < p.nbox_in; q++)                                   // needs every recovered symbol
-                    tma_store_3d(&full_map, slot + size_t(q) * kBoxRows * W, sl * W, q * kBoxRows, int(b));
             bulk_commit();
             bulk_wait_read0();   // the slot's bytes are on their way to L2; it may be overwritten now
         }

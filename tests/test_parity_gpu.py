@@ -311,6 +311,29 @@ def test_user_supplied_non_triangular_code_decodes_but_does_not_encode(tmp_path)
     codec.close()
 
 
+def test_hybrid_does_not_rely_on_zeroed_erasures(codecs, monkeypatch):
+    """Erased positions of the input hold arbitrary bytes instead of zeros: the decoders never read them (the
+    executor's syndromes include them, the elimination stage XORs them out again)."""
+    codec = codecs(1, 64)
+    code = orc.Code.builtin(1)
+    B = 120
+    info = _rand_info(B, codec.k, 64, seed=8)
+    cw = codec.encode(info)
+    mask = codec.gen_erasures(B, 808, P=13)
+    flags = orc.gen_erasures_iid(code.n, 808, B, P=13)
+    rx = _np(cw).copy()
+    junk = np.random.default_rng(3).integers(0, 256, rx.shape, dtype=np.uint8)
+    rx[flags == 1] = junk[flags == 1]
+    rxd = torch.from_numpy(rx).cuda()
+    ref = orc.decode(code, rx, flags, max_iter=10, mode="hybrid")
+    for stages in ("3", "2", "0"):
+        monkeypatch.setenv("LDPC_CUDA_GE_STAGES", stages)
+        out, fail = codec.decode(rxd, mask, max_iter=10, mode="hybrid")
+        good = ref["fail_sys"] == 0
+        assert np.array_equal(_np(fail), ref["fail_sys"])
+        assert np.array_equal(_np(out)[good], _np(info)[good])
+
+
 def test_hybrid_reference_symbol_size(codecs):
     """S = 1024 (the reference's 128 x u64 symbols): the elimination stage walks the payload 64 bytes at a time."""
     codec = codecs(1, 1024, 64)
@@ -400,6 +423,9 @@ def test_hybrid_warp_and_cta_kernels_agree(codecs, monkeypatch):
     for stages in ("0", "2", "1"):          # CTA kernel only / per-warp elimination / inactivation decoding
         monkeypatch.setenv("LDPC_CUDA_GE_STAGES", stages)
         _hybrid_check(codec, code, rx, mask, flags)
+    monkeypatch.setenv("LDPC_CUDA_GE_STAGES", "3")
+    monkeypatch.setenv("LDPC_CUDA_GE_SPLIT", "0")   # inactivation stage as one kernel (pattern + payload together)
+    _hybrid_check(codec, code, rx, mask, flags)
 
 
 @pytest.mark.parametrize("wpc", ["16", "7"])

@@ -50,8 +50,8 @@ def ldpc_case(name, ci, S, B, chan, mode="peel", max_iter=50, reps=3, do_encode=
     pr = codec.profile_read(reset=True); codec.profile_enable(False)
     st = codec.stats()
     ms_parts = {kk: round(pr[kk]["ms"] / reps, 3) for kk in ("peel", "exec_decode")}
-    ms_parts["hybrid"] = round(sum(pr[kk]["ms"] for kk in ("hybrid", "hybrid_warp", "hybrid_cta")) / reps, 3)   # all elimination stages
-    ms_parts["hybrid_stages"] = [round(pr[kk]["ms"] / reps, 3) for kk in ("hybrid", "hybrid_warp", "hybrid_cta")]
+    ms_parts["hybrid"] = round(sum(pr[kk]["ms"] for kk in ("hybrid", "hybrid_apply", "hybrid_warp", "hybrid_cta")) / reps, 3)   # all elimination stages
+    ms_parts["hybrid_stages"] = [round(pr[kk]["ms"] / reps, 3) for kk in ("hybrid", "hybrid_apply", "hybrid_warp", "hybrid_cta")]
     ms = ms_parts["peel"] + ms_parts["exec_decode"] + ms_parts["hybrid"]
     alg = (n * S + (n + 7) // 8 + k * S + 1) * B
     emit(config=name, op="decode", mode=mode, code=ci, S=S, B=B, channel={k_: (list(v) if isinstance(v, tuple) else v) for k_, v in chan.items()},
