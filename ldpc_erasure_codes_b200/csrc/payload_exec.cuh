@@ -170,7 +170,7 @@ payload_exec_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
         mbar_wait(&full[g], phase);
         phase ^= 1u;
         lap(1);
-        if (p.synd) {
+        if (p.synd && reinterpret_cast<const uint32_t *>(blob)[2] != 0u) {   // (uniform over the group)
             // Symbols that stay unknown must read as zero when the syndromes are formed below.  Erased symbols
             // are zero on input by contract; zeroing them here makes the decoder independent of that.
             named_bar_sync(bar_id, GT);
