@@ -61,6 +61,9 @@ static int allow_max_smem(const void *func, int smem_optin)
 static bool ge_split() { const char *e = getenv("LDPC_CUDA_GE_SPLIT"); return !(e && *e == '0'); }
 static int ge_stage_mask() { const char *e = getenv("LDPC_CUDA_GE_STAGES"); return e && *e ? atoi(e) : 3; }
 
+// LDPC_CUDA_TMA4=0: the executor moves its slots box by box (3-D tensor copies only)
+static const bool g_tma4 = [] { const char *e = getenv("LDPC_CUDA_TMA4"); return !(e && *e == '0'); }();
+
 // LDPC_CUDA_DEBUG_SYNC=1: synchronise after every launch so that a faulting kernel is named
 static int debug_sync(const char *what, cudaStream_t st)
 {
@@ -113,6 +116,26 @@ static int make_map(CUtensorMap *map, const void *base, int S, int rows, long lo
                      is_load ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_NONE,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(LDPC_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string(int(r)));
+    return LDPC_OK;
+}
+
+// The same memory seen as [B][nfull][256][S], nfull = rows / 256 whole boxes per codeword: ONE tensor copy with box
+// {W, 256, nfull, 1} moves what nfull 3-D boxes move (the TMA unit takes a few hundred cycles per request; a unit
+// of the executor issued 8 + 6 of them).  Rows past nfull * 256 stay with the 3-D map, whose bounds clip them.
+static int make_map4(CUtensorMap *map, const void *base, int S, int rows, long long B, int W, int nfull, bool is_load)
+{
+    PFN_encodeTiled enc;
+    int rc = get_encode_fn(&enc);
+    if (rc) return rc;
+    cuuint64_t dims[4] = {cuuint64_t(S), cuuint64_t(kBoxRows), cuuint64_t(nfull), cuuint64_t(B)};
+    cuuint64_t strides[3] = {cuuint64_t(S), cuuint64_t(S) * kBoxRows, cuuint64_t(S) * cuuint64_t(rows)};
+    cuuint32_t box[4] = {cuuint32_t(W), cuuint32_t(kBoxRows), cuuint32_t(nfull), 1u};
+    cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void *>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                     is_load ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(LDPC_ERR_CUDA, "cuTensorMapEncodeTiled (4-D) failed with code " + std::to_string(int(r)));
     return LDPC_OK;
 }
 
@@ -418,7 +441,7 @@ extern "C" int ldpc_ctx_set_exec_geometry(ldpc_ctx *c, int slice_bytes, int slot
 // ------------------------------------------------------------------------------------------
 // executor launch
 // ------------------------------------------------------------------------------------------
-typedef void (*ExecKernel)(const CUtensorMap, const CUtensorMap, const ExecParams);
+typedef void (*ExecKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const ExecParams);
 
 // instantiated member counts: 7 / 14 are the committed codes' maximum row weights
 static ExecKernel pick_exec(int W, int max_row_weight, int *rwm_out)
@@ -449,13 +472,17 @@ static int launch_exec(ldpc_ctx *c, const ExecGeom &g, const void *d_in, int row
                        cudaStream_t st, uint8_t *d_synd = nullptr, const uint32_t *d_mask = nullptr)
 {
     if (B <= 0) return LDPC_OK;
-    CUtensorMap in_map, out_map;
+    CUtensorMap in_map, out_map, in4_map, out4_map;
     int rc = make_map(&in_map, d_in, c->S, rows_in, B, g.W, true);
     if (rc) return rc;
     rc = make_map(&out_map, d_out, c->S, rows_out, B, g.W, false);
     if (rc) return rc;
+    const int nfull_in = g_tma4 ? rows_in / kBoxRows : 0, nfull_out = g_tma4 ? rows_out / kBoxRows : 0;
+    in4_map = in_map; out4_map = out_map;      // (placeholders when there is no whole box)
+    if (nfull_in) { rc = make_map4(&in4_map, d_in, c->S, rows_in, B, g.W, nfull_in, true); if (rc) return rc; }
+    if (nfull_out) { rc = make_map4(&out4_map, d_out, c->S, rows_out, B, g.W, nfull_out, false); if (rc) return rc; }
     ExecParams p;
-    p.synd = d_synd; p.mask = d_mask; p.NW = c->NW;
+    p.synd = d_synd; p.mask = d_mask; p.NW = c->NW; p.nfull_in = nfull_in; p.nfull_out = nfull_out;
     p.cidx = c->d_cidx; p.sched = sched; p.sched_len = sched_len; p.B = B; p.sched_stride = sched_stride;
     p.sched_max = g.sched_area; p.m = c->code.m; p.RW = c->code.RW; p.rows_in = rows_in; p.rows_out = rows_out;
     p.nbox_in = (rows_in + kBoxRows - 1) / kBoxRows; p.nbox_out = (rows_out + kBoxRows - 1) / kBoxRows;
@@ -469,7 +496,7 @@ static int launch_exec(ldpc_ctx *c, const ExecGeom &g, const void *d_in, int row
     const int grid = int(std::min<long long>(c->num_sms, B));
     {
         ProfScope ps(c, sched_stride ? LDPC_K_EXEC_DECODE : LDPC_K_EXEC_ENCODE, st);
-        k<<<grid, g.nslot * kExecWarpsPerGroup * 32, g.smem_bytes, st>>>(in_map, out_map, p);
+        k<<<grid, g.nslot * kExecWarpsPerGroup * 32, g.smem_bytes, st>>>(in_map, out_map, in4_map, out4_map, p);
     }
     CUDA_TRY(cudaGetLastError());
     return debug_sync(sched_stride ? "payload_exec_kernel(decode)" : "payload_exec_kernel(encode)", st);

@@ -48,6 +48,7 @@ struct ExecParams {
     uint8_t *synd;              // hybrid mode: [B][m][S] check syndromes of the codewords that still have erasures, or nullptr
     const uint32_t *mask;       // hybrid mode: [B][NW] erasure masks (erased rows are zeroed in the slot before the XOR phase)
     int NW;
+    int nfull_in, nfull_out;    // whole 256-row boxes moved by ONE 4-D tensor copy (map [B][rows/256][256][S]); the rest box by box
     unsigned long long *phase_cycles;  // tuning aid (nullptr = off): [0] claim+issue, [1] load wait, [2] XOR, [3] store, [4] units
 };
 
@@ -70,7 +71,7 @@ __device__ __forceinline__ void sts128(uint32_t addr, const uint4 v)
 template <int W, int RWM>  // W = slice bytes; RWM = members gathered per check (>= max row weight)
 __global__ void __launch_bounds__(kExecMaxGroups *kExecWarpsPerGroup * 32, 1)
 payload_exec_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap out_map,
-                    const ExecParams p)
+                    const __grid_constant__ CUtensorMap in4_map, const __grid_constant__ CUtensorMap out4_map, const ExecParams p)
 {
     constexpr int RWQ = (RWM + 7) / 8;                // uint4 chunks of a padded check row
     constexpr int LPG = W / 16;                       // lanes per entry
@@ -153,7 +154,8 @@ payload_exec_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
                 const int sl = j % p.slices;
                 const uint32_t blen = blen_next;
                 mbar_arrive_expect_tx(&full[g], uint32_t(p.nbox_in) * kBoxRows * W + blen);
-                for (int i = 0; i < p.nbox_in; i++)
+                if (p.nfull_in) tma_load_4d(slot, &in4_map, sl * W, 0, 0, int(b), &full[g]);
+                for (int i = p.nfull_in; i < p.nbox_in; i++)
                     tma_load_3d(slot + size_t(i) * kBoxRows * W, &in_map, sl * W, i * kBoxRows, int(b), &full[g]);
                 if (dynamic) bulk_load_1d(blob, p.sched + b * (long long)p.sched_stride, blen, &full[g]);
                 claim();
@@ -337,7 +339,8 @@ payload_exec_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
         if (leader) {
             const long long b = blockIdx.x + (long long)(j / p.slices) * gridDim.x;
             const int sl = j % p.slices;
-            for (int q = 0; q < p.nbox_out; q++)
+            if (p.nfull_out) tma_store_4d(&out4_map, slot, sl * W, 0, 0, int(b));
+            for (int q = p.nfull_out; q < p.nbox_out; q++)
                 tma_store_3d(&out_map, slot + size_t(q) * kBoxRows * W, sl * W, q * kBoxRows, int(b));
             bulk_commit();
             bulk_wait_read0();   // the slot's bytes are on their way to L2; it may be overwritten now
