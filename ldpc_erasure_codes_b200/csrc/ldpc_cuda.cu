@@ -165,6 +165,12 @@ struct ldpc_ctx {
     unsigned long long *d_phase = nullptr;   // LDPC_CUDA_PHASE_TIMING=1
     uint32_t *d_sim_mask = nullptr;          // ldpc_simulate_fer: masks of one chunk
     unsigned int *d_work_ctr = nullptr;      // peel kernel's codeword claim counter
+    // A peel-mode batch of several max_batch chunks alternates its chunks between two internal streams (and two
+    // sets of the scratch above), so that the tail of one chunk's kernels overlaps the start of the next chunk's.
+    uint8_t *d_sched2 = nullptr; uint32_t *d_sched_len2 = nullptr; uint32_t *d_resid2 = nullptr;
+    uint8_t *d_fail_scratch2 = nullptr; unsigned int *d_work_ctr2 = nullptr;
+    cudaStream_t pstream[2] = {nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
     // geometry
     ExecGeom dec, enc;
     int force_W = 0, force_slots = 0;
@@ -252,6 +258,12 @@ static void free_ctx(ldpc_ctx *c)
     cudaSetDevice(c->device);
     cudaFree(c->d_cidx); cudaFree(c->d_vadj); cudaFree(c->d_enc_blob); cudaFree(c->d_sched);
     cudaFree(c->d_work_ctr);
+    cudaFree(c->d_sched2); cudaFree(c->d_sched_len2); cudaFree(c->d_resid2); cudaFree(c->d_fail_scratch2); cudaFree(c->d_work_ctr2);
+    for (int i = 0; i < 2; i++) {
+        if (c->pstream[i]) cudaStreamDestroy(c->pstream[i]);
+        if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]);
+    }
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     cudaFree(c->d_sched_len); cudaFree(c->d_resid); cudaFree(c->d_stats); cudaFree(c->d_fail_scratch); cudaFree(c->d_phase); cudaFree(c->d_sim_mask);
     hybrid_free(c->hyb);
     for (auto &r : c->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
@@ -600,18 +612,36 @@ extern "C" int ldpc_fill_random(void *d_dst, int64_t nbytes, uint32_t seed, uint
 // ------------------------------------------------------------------------------------------
 // decoder
 // ------------------------------------------------------------------------------------------
+// LDPC_CUDA_CHUNK_PIPELINE=0: chunks of a large batch run one after the other on the caller's stream
+static bool chunk_pipeline() { const char *e = getenv("LDPC_CUDA_CHUNK_PIPELINE"); return !(e && *e == '0'); }
+
+static int ensure_chunk_pipeline(ldpc_ctx *c)
+{
+    if (c->pstream[0]) return LDPC_OK;
+    CUDA_TRY(cudaMalloc(&c->d_sched2, size_t(c->max_batch) * c->sched_stride));
+    CUDA_TRY(cudaMalloc(&c->d_sched_len2, size_t(c->max_batch) * 4));
+    CUDA_TRY(cudaMalloc(&c->d_resid2, size_t(c->max_batch) * 4));
+    CUDA_TRY(cudaMalloc(&c->d_fail_scratch2, size_t(c->max_batch)));
+    CUDA_TRY(cudaMalloc(&c->d_work_ctr2, sizeof(unsigned int)));
+    for (int i = 0; i < 2; i++) CUDA_TRY(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->pstream[1], cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->pstream[0], cudaStreamNonBlocking));
+    return LDPC_OK;
+}
+
 // One peel -> executor (-> elimination) pass over B <= max_batch codewords.  (Cutting a batch into pieces
 // on two internal streams so that one piece's executor overlaps the next one's schedule compiler was
 // measured and is no faster: both kernels fill an SM's shared memory and cannot share one.)
 static int decode_chunk(ldpc_ctx *c, const uint8_t *d_cw, const uint32_t *d_mask, uint8_t *d_out, uint8_t *d_fail,
-                        int max_iter, int mode, long long B, cudaStream_t st)
+                        int max_iter, int mode, long long B, cudaStream_t st, int set = 0)
 {
-    uint8_t *const sched = c->d_sched;
-    uint32_t *const sched_len = c->d_sched_len;
+    uint8_t *const sched = set ? c->d_sched2 : c->d_sched;
+    uint32_t *const sched_len = set ? c->d_sched_len2 : c->d_sched_len;
     PeelParams pp;
     pp.mask = d_mask; pp.sched = sched; pp.sched_len = sched_len;
-    pp.work_ctr = c->d_work_ctr;
-    pp.fail = d_fail ? d_fail : c->d_fail_scratch; pp.resid = c->d_resid; pp.stats = c->d_stats;
+    pp.work_ctr = set ? c->d_work_ctr2 : c->d_work_ctr;
+    pp.fail = d_fail ? d_fail : (set ? c->d_fail_scratch2 : c->d_fail_scratch); pp.resid = set ? c->d_resid2 : c->d_resid; pp.stats = c->d_stats;
     pp.cidx = c->d_cidx; pp.vadj = c->d_vadj; pp.B = B; pp.n = c->code.n; pp.k = c->code.k; pp.m = c->code.m;
     pp.RW = c->code.RW; pp.VW = c->code.VW; pp.NW = c->NW; pp.MW = c->MW; pp.stride = c->sched_stride;
     pp.max_iter = max_iter; pp.rs_n = c->rs_n; pp.rs_k = c->rs_k; pp.groups_per_block = c->peel_groups;
@@ -703,12 +733,25 @@ extern "C" int ldpc_decode(ldpc_ctx *c, const void *d_cw, const uint32_t *d_mask
     const uint8_t *cw = static_cast<const uint8_t *>(d_cw);
     uint8_t *out = static_cast<uint8_t *>(d_out);
     const size_t in_cw = size_t(c->code.n) * c->S, out_cw = size_t(c->code.k) * c->S;
-    for (long long b0 = 0; b0 < B; b0 += c->max_batch) {
+    const bool pipe = mode == LDPC_MODE_PEEL && !c->prof_on && B > c->max_batch && chunk_pipeline();
+    if (pipe) {
+        int rc = ensure_chunk_pipeline(c);
+        if (rc) return rc;
+        CUDA_TRY(cudaEventRecord(c->ev_fork, st));            // both internal streams start after what is queued on st
+        for (int i = 0; i < 2; i++) CUDA_TRY(cudaStreamWaitEvent(c->pstream[i], c->ev_fork, 0));
+    }
+    int idx = 0;
+    for (long long b0 = 0; b0 < B; b0 += c->max_batch, idx++) {
         const long long nb = std::min<long long>(c->max_batch, B - b0);
         int rc = decode_chunk(c, cw + size_t(b0) * in_cw, d_mask + size_t(b0) * c->NW, out + size_t(b0) * out_cw,
-                              d_fail ? d_fail + b0 : nullptr, max_iter, mode, nb, st);
+                              d_fail ? d_fail + b0 : nullptr, max_iter, mode, nb, pipe ? c->pstream[idx & 1] : st, pipe ? (idx & 1) : 0);
         if (rc) return rc;
     }
+    if (pipe)
+        for (int i = 0; i < 2; i++) {                          // st continues when both are done
+            CUDA_TRY(cudaEventRecord(c->ev_join[i], c->pstream[i]));
+            CUDA_TRY(cudaStreamWaitEvent(st, c->ev_join[i], 0));
+        }
     return LDPC_OK;
 }
 

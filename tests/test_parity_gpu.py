@@ -182,6 +182,27 @@ def test_ragged_batches_and_chunking(codecs, B):
     assert np.array_equal(_np(fail), ref["fail_sys"]) and np.array_equal(_np(out), ref["out"])
 
 
+def test_chunk_pipeline_matches_serial(codecs, monkeypatch):
+    """A batch of several max_batch chunks alternates between two internal streams; same bytes as chunk after chunk,
+    and the caller's stream sees the results when the call's work is done."""
+    codec = codecs(1, 32, 512)
+    code = orc.Code.builtin(1)
+    B = 512 * 5 + 77
+    info = _rand_info(B, codec.k, 32, seed=21)
+    cw = codec.encode(info)
+    rx = cw.clone()
+    mask = codec.gen_erasures(B, 2121, P=12, payload=rx)
+    out1, f1 = codec.decode(rx, mask)
+    chk = out1.sum(dtype=torch.int64)                  # queued on the caller's stream right behind the call
+    monkeypatch.setenv("LDPC_CUDA_CHUNK_PIPELINE", "0")
+    out2, f2 = codec.decode(rx, mask)
+    assert int(chk) == int(out2.sum(dtype=torch.int64))
+    assert torch.equal(out1, out2) and torch.equal(f1, f2)
+    flags = orc.gen_erasures_iid(code.n, 2121, B, P=12)
+    ref = orc.decode(code, _np(rx), flags, max_iter=50, mode="peel")
+    assert np.array_equal(_np(f1), ref["fail_sys"]) and np.array_equal(_np(out1), ref["out"])
+
+
 @pytest.mark.parametrize("W,slots", [(16, 0), (32, 0), (64, 0), (32, 1), (32, 2), (16, 2)])
 def test_executor_geometries_agree(codecs, W, slots):
     from ldpc_erasure_codes_b200.codec import LdpcCodec
