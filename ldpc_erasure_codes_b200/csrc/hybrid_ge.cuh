@@ -906,54 +906,76 @@ __global__ void __launch_bounds__(512) hybrid_apply_kernel(const GeWarpParams q)
             __syncwarp();
             lap(1);
             // ---- phase 1 replay: b[row] ^= b[pivot] for the other rows of each peeled unknown, in order ----
+            // 32 steps at a time: lane t fetches step t's pivot and the rows of its unknown (one 8- or 16-byte
+            // load); the steps then run one after the other with their operands coming from shuffles, so that
+            // the only memory round trip in a step is the row update itself.
             for (int i0 = 0; i0 < npeel; i0 += 32) {
-                const int mycol = (i0 + lane < npeel) ? pl_col[i0 + lane] : 0;
-                const int myrow = (i0 + lane < npeel) ? pl_row[i0 + lane] : 0;
+                const bool mine = i0 + lane < npeel;
+                const int mycol = mine ? pl_col[i0 + lane] : 0;
+                const int myrow = mine ? pl_row[i0 + lane] : 0;
+                uint32_t nw[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};   // up to 8 rows, two per word
+                if (mine) {
+                    const uint32_t *nr = reinterpret_cast<const uint32_t *>(nbr + size_t(mycol) * VW);
+#pragma unroll
+                    for (int w = 0; w < 4; w++) if (2 * w < VW) nw[w] = nr[w];
+                }
                 const int cnt = min(32, npeel - i0);
                 for (int t = 0; t < cnt; t++) {
-                    const int col = __shfl_sync(FULL, mycol, t), ri = __shfl_sync(FULL, myrow, t);
-                    uint32_t rj = 0xFFFFu;
-                    if (lane < VW) rj = nbr[col * VW + lane];
-                    const unsigned hb = __ballot_sync(FULL, rj != 0xFFFFu && int(rj) != ri);
-                    if (!hb) continue;
-                    const uint4 pb = *reinterpret_cast<const uint4 *>(bmat + size_t(ri) * 16 + qd * 4);
-                    const int nh = __popc(hb);
-                    for (int h0 = 0; h0 < nh; h0 += 8) {
-                        const int src = __fns(hb, 0, h0 + hs + 1);       // lane holding the (h0+hs)-th hit, -1 if none
-                        const int r2 = __shfl_sync(FULL, int(rj), src < 0 ? 0 : src);
-                        if (src >= 0 && src < 32 && qd < nq) {
-                            uint4 *br = reinterpret_cast<uint4 *>(bmat + size_t(r2) * 16 + qd * 4);
-                            uint4 a4 = *br;
-                            a4.x ^= pb.x; a4.y ^= pb.y; a4.z ^= pb.z; a4.w ^= pb.w;
-                            *br = a4;
-                        }
+                    const int ri = __shfl_sync(FULL, myrow, t);
+                    const uint32_t w0 = __shfl_sync(FULL, nw[0], t), w1 = __shfl_sync(FULL, nw[1], t);
+                    const uint32_t w2 = __shfl_sync(FULL, nw[2], t), w3 = __shfl_sync(FULL, nw[3], t);
+                    const uint32_t wsel = (hs >> 1) == 0 ? w0 : ((hs >> 1) == 1 ? w1 : ((hs >> 1) == 2 ? w2 : w3));
+                    const uint32_t r2 = (hs & 1) ? (wsel >> 16) : (wsel & 0xFFFFu);       // hit slot hs of this step
+                    if (r2 != 0xFFFFu && int(r2) != ri && qd < nq) {
+                        const uint4 pb = *reinterpret_cast<const uint4 *>(bmat + size_t(ri) * 16 + qd * 4);
+                        uint4 *br = reinterpret_cast<uint4 *>(bmat + size_t(r2) * 16 + qd * 4);
+                        uint4 a4 = *br;
+                        a4.x ^= pb.x; a4.y ^= pb.y; a4.z ^= pb.z; a4.w ^= pb.w;
+                        *br = a4;
                     }
                     __syncwarp();
                 }
             }
             lap(2);
             // ---- phase 2: dense solve on [ipart | b] of the unused rows (the plan is known to have full rank) ----
+            // Only the rows no peeled unknown used as its pivot take part: R - npeel of them, listed once.
+            uint16_t *ulist = inv_rowmap;                 // (the inverse row map is not needed in this kernel)
+            int nU = 0;
+            for (int r0 = 0; r0 < R; r0 += 32) {
+                const int r = r0 + lane;
+                const bool un = r < R && !(state[r] & USED);
+                const unsigned bal = __ballot_sync(FULL, un);
+                if (un) ulist[nU + __popc(bal & ((1u << lane) - 1u))] = uint16_t(r);
+                nU += __popc(bal);
+            }
+            __syncwarp();
             for (int c = 0; c < ninact; c++) {
                 unsigned best = 0xFFFFFFFFu;
-                for (int r0 = lane; r0 < R; r0 += 32)
-                    if (!(state[r0] & (USED | TAKEN)) && ((ipart[r0] >> c) & 1u)) { best = uint32_t(r0); break; }
+                for (int i = lane; i < nU; i += 32) {
+                    const int r = ulist[i];
+                    if (!(state[r] & TAKEN) && ((ipart[r] >> c) & 1u)) { best = uint32_t(r); break; }
+                }
                 best = __reduce_min_sync(FULL, best);
                 if (best == 0xFFFFFFFFu) break;                           // (cannot happen: the pattern kernel found the pivots)
                 const int pr = int(best);
                 const unsigned long long pI = ipart[pr];
-                uint32_t pb = 0u;
-                if (lane < 16) pb = bmat[size_t(pr) * 16 + lane];
+                uint4 pb = make_uint4(0u, 0u, 0u, 0u);
+                if (qd < nq) pb = *reinterpret_cast<const uint4 *>(bmat + size_t(pr) * 16 + qd * 4);
                 __syncwarp();
                 if (lane == 0) { state[pr] |= TAKEN; ipiv[c] = uint16_t(pr); }
-                for (int r0 = 0; r0 < R; r0 += 32) {
-                    const int r2 = r0 + lane;
-                    const bool hit = r2 < R && r2 != pr && !(state[r2] & USED) && ((ipart[r2] >> c) & 1u);
-                    if (hit) ipart[r2] ^= pI;
-                    unsigned hb = __ballot_sync(FULL, hit);
-                    while (hb) {
-                        const int hl = __ffs(hb) - 1;
-                        hb &= hb - 1u;
-                        if (lane < 16) bmat[size_t(r0 + hl) * 16 + lane] ^= pb;
+                for (int i0 = 0; i0 < nU; i0 += 8) {      // four lanes per row: test, then one quarter of b each
+                    const int r2 = ulist[min(i0 + hs, nU - 1)];
+                    const unsigned long long ip = ipart[r2];
+                    const bool hit = i0 + hs < nU && r2 != pr && ((ip >> c) & 1u);
+                    __syncwarp();                          // (all four lanes have read ipart[r2])
+                    if (hit) {
+                        if (qd == 0) ipart[r2] = ip ^ pI;
+                        if (qd < nq) {
+                            uint4 *br = reinterpret_cast<uint4 *>(bmat + size_t(r2) * 16 + qd * 4);
+                            uint4 a4 = *br;
+                            a4.x ^= pb.x; a4.y ^= pb.y; a4.z ^= pb.z; a4.w ^= pb.w;
+                            *br = a4;
+                        }
                     }
                 }
                 __syncwarp();
