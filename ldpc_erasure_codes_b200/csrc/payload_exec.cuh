@@ -249,15 +249,17 @@ payload_exec_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
                 }
                 c_dt = done_base + uint32_t(inc - nw);
                 done_base += uint32_t(__shfl_sync(FULLM, inc, 31));
-                todo = __ballot_sync(FULLM, ll < nl && ((wg + ll) % WPGc) * EPW < cnt);
+                // a level's first entries go to the warp after the last worker of the level below (c_dt counts
+                // the workers so far): two-warp levels then alternate between the warp pairs, and a warp's
+                // preparation for its next level overlaps the other pair's turn
+                todo = __ballot_sync(FULLM, ll < nl && int((uint32_t(wg) - c_dt) % WPGc) * EPW < cnt);
             }
             const int b = __ffs(todo) - 1;
             todo &= todo - 1u;
-            const int l = l0 + b;
             const int s0 = __shfl_sync(FULLM, c_s0, b);
             t_end = __shfl_sync(FULLM, c_s1, b);
             done_target = __shfl_sync(FULLM, c_dt, b);
-            t_idx = s0 + ((wg + l) % WPGc) * EPW + es;
+            t_idx = s0 + int((uint32_t(wg) - done_target) % WPGc) * EPW + es;
             t_valid = t_idx < t_end;
             if (t_valid) prepare();
             return true;
