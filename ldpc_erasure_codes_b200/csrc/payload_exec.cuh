@@ -184,11 +184,11 @@ payload_exec_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
 
         // ---- XOR the schedule into the slot -----------------------------------------------
         // The level walk is a chain of shared-memory round trips (a level's gathers cannot start
-        // before the previous level's results are written, ~500 cycles per level all told), so:
+        // before the previous level's results are written, ~600-700 cycles per level all told), so:
         //  * everything that does NOT depend on the payload -- which entry a lane group handles
         //    next, the check's member list, the members' shared addresses -- is prepared ahead;
-        //  * consecutive small levels go to different warps of the group (entry slots rotate by one
-        //    warp per level), and there is NO group-wide barrier between levels: a warp that finishes
+        //  * consecutive levels go to different warps of the group (a level starts at the warp after the
+        //    last worker of the level below), and there is NO group-wide barrier between levels: a warp that finishes
         //    its part of level l bumps a completion counter (release) and goes on to prepare its next
         //    task; a warp about to execute level L spins (acquire) until the counter shows that all
         //    workers of the levels below are done.
