@@ -173,6 +173,7 @@ int ldpc_reset_stats(ldpc_ctx *ctx);
  * when enabled, every kernel the context launches is bracketed by CUDA events on the
  * launching stream; ldpc_profile_read() synchronises and returns per-kernel device time.
  * Launch counters are always maintained.                                                 */
+/* (LDPC_K_CHANNEL also covers the packet front-end kernels) */
 enum { LDPC_K_PEEL = 0, LDPC_K_EXEC_DECODE = 1, LDPC_K_EXEC_ENCODE = 2,
        LDPC_K_HYBRID = 3,        /* elimination stage 1: inactivation decoding, one warp per codeword (pattern part) */
        LDPC_K_CHANNEL = 4,
@@ -207,6 +208,28 @@ int ldpc_decode_host(ldpc_ctx *ctx, const void *h_cw, const uint32_t *h_mask, vo
  * block0): bench / test input generator, independent of batch sharding.                  */
 int ldpc_fill_random(void *d_dst, int64_t nbytes, uint32_t seed, uint64_t block0, int device,
                      void *stream);
+
+/* ---- FEC packet front-ends ----------------------------------------
+ * The reference's sender and receiver wrap every symbol in a packet: one 64-bit FEC header word
+ * -- the 32-bit value [class:8 | block:8 | symbol:16] repeated in both halves, class code 1 --
+ * followed by the S-byte symbol (OpenCL/device/ldpc_erasure_encoder_VITA_in_UDP_out.cl:100-104,
+ * 170-175; OpenCL/device/ldpc_erasure_decoder_with_reordering_logic.cl:77-84).
+ *   ldpc_packetize    codewords [B][n][S] -> packets [B*n][8+S], block numbers block0 + b (mod 256).
+ *   ldpc_depacketize  packets [n_packets][8+S] in ANY order, with losses and duplicates -> codewords
+ *                     [B][n][S] (missing symbols all-zero) + erasure mask (bit set = not received):
+ *                     what ldpc_decode takes.  A packet belongs to the window iff
+ *                     (block - block0) mod 256 < B (B <= 256) and symbol < n, class 1 and both header
+ *                     halves equal; others are dropped (receiver :105,124).  d_counts[b] = packets
+ *                     placed for block b (duplicates counted, like cur_block_num_cnt :117),
+ *                     d_counts[B] = dropped packets.
+ *   ldpc_ready_to_decode  the receiver's hand-off rule (:54-55,139): all n symbols in, or more than
+ *                     k + round(0.8 m) with > 10 packets of the next block seen, or more than
+ *                     k + round(0.2 m) with > 100.                                                 */
+#define LDPC_FEC_CLASS 1
+int ldpc_packetize(ldpc_ctx *ctx, const void *d_cw, uint32_t block0, int64_t B, void *d_packets, void *stream);
+int ldpc_depacketize(ldpc_ctx *ctx, const void *d_packets, int64_t n_packets, uint32_t block0, int64_t B,
+                     void *d_cw, uint32_t *d_mask, uint32_t *d_counts, void *stream);
+int ldpc_ready_to_decode(const ldpc_ctx *ctx, int cur_block_cnt, int next_block_cnt);
 
 /* ---- Reed-Solomon GF(2^8) comparison code -------------------------------------------
  * Field polynomial 0x171, alpha = 2 (Matlab/Build_GF256_Lookup_Tables.m:11-24);

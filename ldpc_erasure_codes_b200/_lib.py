@@ -12,7 +12,7 @@ SO_PATH = os.path.join(HERE, "libldpc_cuda.so")
 EXPORTS = [
     "ldpc_ctx_create", "ldpc_ctx_destroy", "ldpc_ctx_info", "ldpc_read_h_file", "ldpc_ctx_get_csr", "ldpc_ctx_set_exec_geometry",
     "ldpc_encode", "ldpc_gen_erasures", "ldpc_decode", "ldpc_simulate_fer", "ldpc_get_stats", "ldpc_reset_stats",
-    "ldpc_encode_host", "ldpc_decode_host", "ldpc_fill_random", "ldpc_profile_enable", "ldpc_profile_read",
+    "ldpc_encode_host", "ldpc_decode_host", "ldpc_fill_random", "ldpc_packetize", "ldpc_depacketize", "ldpc_ready_to_decode", "ldpc_profile_enable", "ldpc_profile_read",
     "rs_ctx_create", "rs_ctx_destroy", "rs_ctx_get_generator", "rs_encode", "rs_decode",
     "ldpc_last_error_string", "ldpc_cuda_abi_version",
 ]
@@ -75,6 +75,9 @@ def load():
     lib.ldpc_encode_host.argtypes = [vp, vp, vp, i64]
     lib.ldpc_decode_host.argtypes = [vp, vp, vp, vp, vp, i32, i32, i64]
     lib.ldpc_fill_random.argtypes = [vp, i64, u32, u64, i32, vp]
+    lib.ldpc_packetize.argtypes = [vp, vp, u32, i64, vp, vp]
+    lib.ldpc_depacketize.argtypes = [vp, vp, i64, u32, i64, vp, vp, vp, vp]
+    lib.ldpc_ready_to_decode.argtypes = [vp, i32, i32]
     lib.ldpc_profile_enable.argtypes = [vp, i32]
     lib.ldpc_profile_read.argtypes = [vp, C.POINTER(Profile), i32]
     lib.rs_ctx_create.argtypes = [C.POINTER(vp), i32, i32, i32, i32, i64]

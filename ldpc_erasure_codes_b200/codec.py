@@ -129,6 +129,28 @@ class LdpcCodec:
                                         {"peel": MODE_PEEL, "hybrid": MODE_HYBRID}[mode], B, _stream()))
         return out, fail
 
+    # ---- FEC packet front-ends (encoder_VITA_in_UDP_out.cl / decoder_with_reordering_logic.cl) ----
+    def packetize(self, cw: torch.Tensor, block0: int = 0) -> torch.Tensor:
+        """cw [B][n][S] -> packets [B*n][8+S]: 64-bit FEC header word [class|block|symbol] x2, then the symbol."""
+        assert cw.is_cuda and cw.dtype == torch.uint8 and cw.is_contiguous() and cw.shape[1:] == (self.n, self.S)
+        B = cw.shape[0]
+        pk = torch.empty((B * self.n, 8 + self.S), dtype=torch.uint8, device=cw.device)
+        _lib.check(self.lib.ldpc_packetize(self._h, _ptr(cw), block0 & 0xFFFFFFFF, B, _ptr(pk), _stream()))
+        return pk
+
+    def depacketize(self, packets: torch.Tensor, block0: int, B: int):
+        """packets [N][8+S] in arrival order -> (cw [B][n][S], mask [B][mask_words], counts [B+1])."""
+        assert packets.is_cuda and packets.dtype == torch.uint8 and packets.is_contiguous() and packets.shape[1] == 8 + self.S
+        cw = torch.empty((B, self.n, self.S), dtype=torch.uint8, device=packets.device)
+        mask = torch.empty((B, self.mask_words), dtype=torch.int32, device=packets.device)
+        counts = torch.empty((B + 1,), dtype=torch.int32, device=packets.device)
+        _lib.check(self.lib.ldpc_depacketize(self._h, _ptr(packets), packets.shape[0], block0 & 0xFFFFFFFF, B, _ptr(cw), _ptr(mask),
+                                             _ptr(counts), _stream()))
+        return cw, mask, counts
+
+    def ready_to_decode(self, cur_block_cnt: int, next_block_cnt: int) -> bool:
+        return bool(self.lib.ldpc_ready_to_decode(self._h, cur_block_cnt, next_block_cnt))
+
     # ---- run(): host buffers in, host buffers out ---------------------------------------
     def decode_host(self, cw: torch.Tensor, mask: torch.Tensor, max_iter=50, mode="peel", out=None, fail=None):
         """cw / mask are HOST tensors (pinned for overlap); copies happen inside the call."""

@@ -17,6 +17,7 @@
 #include "../../include/ldpc_cuda.h"
 #include "erasure_gen.cuh"
 #include "hmat.hpp"
+#include "fec_packets.cuh"
 #include "hybrid_ge.cuh"
 #include "payload_exec.cuh"
 #include "peel_schedule.cuh"
@@ -607,6 +608,75 @@ extern "C" int ldpc_fill_random(void *d_dst, int64_t nbytes, uint32_t seed, uint
     fill_random_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<uint4 *>(d_dst), nblocks, seed, block0);
     CUDA_TRY(cudaGetLastError());
     return LDPC_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// FEC packet front-ends
+// ------------------------------------------------------------------------------------------
+extern "C" int ldpc_packetize(ldpc_ctx *c, const void *d_cw, uint32_t block0, int64_t B, void *d_packets, void *stream)
+{
+    if (!c || B < 0) return fail(LDPC_ERR_ARG, "bad argument to ldpc_packetize");
+    if (B == 0) return LDPC_OK;
+    if (!d_cw || !d_packets) return fail(LDPC_ERR_ARG, "NULL buffer passed to ldpc_packetize");
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long np = (long long)B * c->code.n;
+    const int words = c->S / 8;
+    const int lpp = words >= 32 ? 32 : (words >= 8 ? 8 : (words >= 4 ? 4 : 2));
+    const int grid = int(std::min<long long>((np * lpp + 255) / 256, (long long)c->num_sms * 32));
+    ProfScope ps(c, LDPC_K_CHANNEL, st);
+    auto go = [&](auto kern) {
+        kern<<<grid, 256, 0, st>>>(static_cast<const unsigned long long *>(d_cw), static_cast<unsigned long long *>(d_packets), np, c->code.n,
+                                   words, block0);
+    };
+    if (lpp == 32) go(packetize_kernel<32>);
+    else if (lpp == 8) go(packetize_kernel<8>);
+    else if (lpp == 4) go(packetize_kernel<4>);
+    else go(packetize_kernel<2>);
+    CUDA_TRY(cudaGetLastError());
+    return LDPC_OK;
+}
+
+extern "C" int ldpc_depacketize(ldpc_ctx *c, const void *d_packets, int64_t n_packets, uint32_t block0, int64_t B,
+                                void *d_cw, uint32_t *d_mask, uint32_t *d_counts, void *stream)
+{
+    if (!c || B < 0 || n_packets < 0) return fail(LDPC_ERR_ARG, "bad argument to ldpc_depacketize");
+    if (B > 256) return fail(LDPC_ERR_ARG, "ldpc_depacketize: block numbers are modulo 256, a window holds at most 256 blocks");
+    if (B == 0) return LDPC_OK;
+    if (!d_cw || !d_mask || !d_counts || (n_packets > 0 && !d_packets)) return fail(LDPC_ERR_ARG, "NULL buffer passed to ldpc_depacketize");
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int words = c->S / 8;
+    CUDA_TRY(cudaMemsetAsync(d_cw, 0, size_t(B) * c->code.n * c->S, st));       // missing symbols are all-zero (receiver :59-68)
+    {
+        ProfScope ps(c, LDPC_K_CHANNEL, st);
+        const int grid = int(std::min<long long>((B * c->NW + 255) / 256, (long long)c->num_sms * 8));
+        fec_mask_init_kernel<<<grid, 256, 0, st>>>(d_mask, B, c->code.n, c->NW, d_counts);
+    }
+    CUDA_TRY(cudaGetLastError());
+    if (n_packets > 0) {
+        ProfScope ps(c, LDPC_K_CHANNEL, st);
+        const int lpp = words >= 32 ? 32 : (words >= 8 ? 8 : (words >= 4 ? 4 : 2));
+        const int grid = int(std::min<long long>((n_packets * lpp + 255) / 256, (long long)c->num_sms * 32));
+        auto args = [&](auto kern) {
+            kern<<<grid, 256, 0, st>>>(static_cast<const unsigned long long *>(d_packets), n_packets, static_cast<unsigned long long *>(d_cw),
+                                       d_mask, d_counts, B, c->code.n, c->NW, words, block0);
+        };
+        if (lpp == 32) args(depacketize_kernel<32>);
+        else if (lpp == 8) args(depacketize_kernel<8>);
+        else if (lpp == 4) args(depacketize_kernel<4>);
+        else args(depacketize_kernel<2>);
+        CUDA_TRY(cudaGetLastError());
+    }
+    return debug_sync("depacketize_kernel", st);
+}
+
+extern "C" int ldpc_ready_to_decode(const ldpc_ctx *c, int cur_block_cnt, int next_block_cnt)
+{
+    if (!c) return 0;
+    const int n = c->code.n, k = c->code.k, m = n - k;
+    const int desired = int(double(m) * 0.8 + 0.5), minimum = int(double(m) * 0.2 + 0.5);
+    return (cur_block_cnt == n) || (cur_block_cnt > k + desired && next_block_cnt > 10) || (cur_block_cnt > k + minimum && next_block_cnt > 100);
 }
 
 // ------------------------------------------------------------------------------------------

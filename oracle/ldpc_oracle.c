@@ -642,3 +642,65 @@ void orc_ldpc_encode_batch(int n, int k, const int32_t *row_ptr, const int32_t *
     for (int64_t b = 0; b < B; b++)
         orc_ldpc_encode(n, k, row_ptr, col_idx, S, info + (size_t)b * k * S, cw + (size_t)b * n * S);
 }
+
+/* ------------------------------------------------------------------------- */
+/* FEC packet front-ends.                                */
+/* Packet = one 64-bit FEC header word + the S-byte symbol.  Header: the      */
+/* 32-bit value [class:8 | block:8 | symbol:16] repeated in both halves,      */
+/* OpenCL/device/ldpc_erasure_encoder_VITA_in_UDP_out.cl:100-104 (repair       */
+/* symbols) and :170-175 (source symbols); class code 1 (:57).  Receiver:      */
+/* OpenCL/device/ldpc_erasure_decoder_with_reordering_logic.cl:77-84 parses    */
+/* (hdr >> 24) & 0xff, (hdr >> 16) & 0xff, hdr & 0xffff; a block buffer starts */
+/* all-erased and all-zero (:59-68); a received symbol is stored at its        */
+/* symbol number and its flag cleared (:94-131); packets of blocks outside     */
+/* the window are dropped (:105,124).  The reference's window is {current,     */
+/* next}; here it is [block0, block0 + B) modulo 256.  A packet counts for     */
+/* its block every time it arrives (cur_block_num_cnt, :117), duplicates too.  */
+/* ------------------------------------------------------------------------- */
+static uint64_t orc_fec_header(uint32_t cls, uint32_t block, uint32_t symbol)
+{
+    const uint64_t d = 0xffffffffull & (((uint64_t)(cls & 0xffu) << 24) | ((uint64_t)(block & 0xffu) << 16) | (symbol & 0xffffu));
+    return ((d << 32) & 0xffffffff00000000ull) | d;
+}
+
+void orc_packetize(int n, int S, uint32_t block0, int64_t B, const uint8_t *cw, uint8_t *packets)
+{
+    const size_t ps = 8 + (size_t)S;
+    for (int64_t b = 0; b < B; b++)
+        for (int s = 0; s < n; s++) {
+            uint8_t *p = packets + ((size_t)b * n + s) * ps;
+            const uint64_t h = orc_fec_header(1u, block0 + (uint32_t)b, (uint32_t)s);
+            memcpy(p, &h, 8);
+            memcpy(p + 8, cw + ((size_t)b * n + s) * S, (size_t)S);
+        }
+}
+
+/* cw [B][n][S] (zeroed, then filled), flags [B][n] (1 = erased), counts [B+1] ([B] = dropped packets) */
+void orc_depacketize(int n, int S, uint32_t block0, int64_t B, const uint8_t *packets, int64_t npackets,
+                     uint8_t *cw, uint8_t *flags, uint32_t *counts)
+{
+    const size_t ps = 8 + (size_t)S;
+    memset(cw, 0, (size_t)B * n * S);
+    memset(flags, 1, (size_t)B * n);
+    memset(counts, 0, (size_t)(B + 1) * 4);
+    for (int64_t i = 0; i < npackets; i++) {
+        const uint8_t *p = packets + (size_t)i * ps;
+        uint64_t h;
+        memcpy(&h, p, 8);
+        const uint32_t lo = (uint32_t)h, hi = (uint32_t)(h >> 32);
+        const uint32_t cls = (lo >> 24) & 0xffu, blk = (lo >> 16) & 0xffu, sym = lo & 0xffffu;
+        const uint32_t rel = (blk - block0) & 0xffu;
+        if (lo != hi || cls != 1u || (int64_t)rel >= B || (int)sym >= n) { counts[B]++; continue; }
+        memcpy(cw + ((size_t)rel * n + sym) * S, p + 8, (size_t)S);
+        flags[(size_t)rel * n + sym] = 0;
+        counts[rel]++;
+    }
+}
+
+/* hand-off rule of the receiver, ldpc_erasure_decoder_with_reordering_logic.cl:54-55,139 */
+int orc_ready_to_decode(int n, int k, int cur_cnt, int next_cnt)
+{
+    const int m = n - k;
+    const int desired = (int)((double)m * 0.8 + 0.5), minimum = (int)((double)m * 0.2 + 0.5);   /* round() */
+    return (cur_cnt == n) || ((cur_cnt > k + desired) && (next_cnt > 10)) || ((cur_cnt > k + minimum) && (next_cnt > 100));
+}

@@ -201,5 +201,30 @@ def rs_decode(G, recv_idx, recv_val):
     return out, rc
 
 
+# ---- FEC packet front-ends ---------------------------------------------------------
+def packetize(cw: np.ndarray, block0: int) -> np.ndarray:
+    """cw [B][n][S] -> packets [B*n][8+S] (encoder_VITA_in_UDP_out.cl:100-104,170-175)."""
+    B, n, S = cw.shape
+    out = np.zeros((B * n, 8 + S), dtype=np.uint8)
+    lib().orc_packetize(C.c_int(n), C.c_int(S), C.c_uint32(block0), C.c_int64(B), _p(np.ascontiguousarray(cw)), _p(out))
+    return out
+
+
+def depacketize(packets: np.ndarray, n: int, block0: int, B: int):
+    """packets [N][8+S] in arrival order -> (cw [B][n][S], flags [B][n], counts [B+1]) (decoder_with_reordering_logic.cl:59-131)."""
+    packets = np.ascontiguousarray(packets)
+    N, ps = packets.shape
+    S = ps - 8
+    cw = np.zeros((B, n, S), dtype=np.uint8)
+    flags = np.zeros((B, n), dtype=np.uint8)
+    counts = np.zeros(B + 1, dtype=np.uint32)
+    lib().orc_depacketize(C.c_int(n), C.c_int(S), C.c_uint32(block0), C.c_int64(B), _p(packets), C.c_int64(N), _p(cw), _p(flags), _p(counts))
+    return cw, flags, counts
+
+
+def ready_to_decode(n, k, cur_cnt, next_cnt) -> bool:
+    return bool(lib().orc_ready_to_decode(C.c_int(n), C.c_int(k), C.c_int(cur_cnt), C.c_int(next_cnt)))
+
+
 def num_threads():
     return lib().orc_num_threads()

@@ -302,3 +302,36 @@ def test_mds_count():
     er[:64] = 1          # block 0: 64 > 63 -> fail
     er[255:255 + 63] = 1  # block 1: 63 -> ok
     assert orc.rs_mds_count(2040, 255, 192, er) == 1
+
+
+# ---------------------------------------------------------------------------- FEC packet front-ends
+def test_fec_packet_format_and_reassembly():
+    """Header word = [class:8|block:8|symbol:16] in both halves (encoder_VITA_in_UDP_out.cl:100-104,170-175); the receiver
+    places a symbol by its header, clears its flag, drops foreign blocks (decoder_with_reordering_logic.cl:77-131)."""
+    rng = np.random.default_rng(7)
+    B, n, S = 4, 37, 16
+    cw = rng.integers(0, 256, (B, n, S), dtype=np.uint8)
+    pk = orc.packetize(cw, block0=254)                       # blocks 254, 255, 0, 1: the counter is modulo 256
+    assert pk.shape == (B * n, 8 + S)
+    hdr = pk[:, :8].copy().view("<u8").ravel()
+    assert hdr[0] == 0x01FE000001FE0000 and hdr[n + 5] == 0x01FF000501FF0005 and hdr[2 * n + 36] == 0x0100002401000024
+    assert np.array_equal(pk[:, 8:].reshape(B, n, S), cw)
+    # arrival order does not matter; lost packets stay erased and zero; duplicates count twice; foreign packets are dropped
+    order = rng.permutation(B * n)
+    lost = rng.random(B * n) < 0.2
+    stream = np.concatenate([pk[order][~lost[order]], pk[:3], orc.packetize(cw[:1], block0=77)[:5]])
+    bad = pk[10:11].copy(); bad[0, 3] ^= 0xFF                # class byte of the low half corrupted: halves differ
+    stream = np.concatenate([stream, bad])
+    got, flags, counts = orc.depacketize(stream, n, 254, B)
+    want = cw.copy(); want.reshape(B * n, S)[lost & (np.arange(B * n) >= 3)] = 0
+    assert np.array_equal(got, want)
+    assert np.array_equal(flags.ravel(), (lost & (np.arange(B * n) >= 3)).astype(np.uint8))
+    assert counts[B] == 6 and counts[:B].sum() == (~lost).sum() + 3
+
+
+def test_receiver_hand_off_rule():
+    """decoder_with_reordering_logic.cl:54-55,139 for the reference's (2000,1000): desired 800, minimum 200."""
+    r = lambda cur, nxt: orc.ready_to_decode(2000, 1000, cur, nxt)
+    assert r(2000, 0) and not r(1999, 0)
+    assert r(1801, 11) and not r(1800, 11) and not r(1801, 10)
+    assert r(1201, 101) and not r(1200, 101) and not r(1201, 100)

@@ -573,3 +573,55 @@ def test_simulate_fer_bursty_channel_and_host_hybrid(codecs):
     out_h, fail_h = codec.decode_host(rx.cpu().pin_memory(), mask.cpu().pin_memory(), max_iter=10, mode="hybrid")
     ref = orc.decode(code, _np(rx), flags, max_iter=10, mode="hybrid")
     assert np.array_equal(out_h.numpy(), ref["out"]) and np.array_equal(fail_h.numpy(), ref["fail_sys"])
+
+
+# ------------------------------------------------------------------------------- FEC packet front-ends
+@pytest.mark.parametrize("ci,S,B,block0", [(1, 64, 6, 0), (1, 16, 9, 250), (0, 1024, 2, 255), (2, 32, 3, 17)])
+def test_packetize_and_depacketize_bit_exact(codecs, ci, S, B, block0):
+    """Sender / receiver data formats of the reference's front-end kernels against the oracle: any arrival order, losses,
+    duplicates, packets of foreign blocks, a corrupted header; block numbers wrap modulo 256."""
+    from ldpc_erasure_codes_b200.codec import unpack_mask
+    codec = codecs(ci, S)
+    n = codec.n
+    cw = _rand_info(B, n, S, seed=5 + ci)
+    pk = codec.packetize(cw, block0)
+    ref_pk = orc.packetize(_np(cw), block0)
+    assert np.array_equal(_np(pk), ref_pk)
+    rng = np.random.default_rng(9)
+    order = rng.permutation(B * n)
+    keep = rng.random(B * n) >= 0.25
+    foreign = orc.packetize(_np(cw[:1]), (block0 + B + 40) & 0xFF)[:50]
+    bad = ref_pk[7:8].copy(); bad[0, 7] ^= 0x01
+    stream = np.concatenate([ref_pk[order][keep[order]], ref_pk[:11], foreign, bad])
+    got_cw, got_mask, got_cnt = codec.depacketize(torch.from_numpy(stream).cuda(), block0, B)
+    ref_cw, ref_flags, ref_cnt = orc.depacketize(stream, n, block0, B)
+    assert np.array_equal(_np(got_cw), ref_cw)
+    assert np.array_equal(unpack_mask(got_mask, n), ref_flags)
+    assert np.array_equal(_np(got_cnt).astype(np.uint32), ref_cnt) and ref_cnt[B] == 51
+    # nothing received at all: everything erased, zero payload
+    e_cw, e_mask, e_cnt = codec.depacketize(torch.zeros((0, 8 + S), dtype=torch.uint8, device="cuda"), block0, B)
+    assert not _np(e_cw).any() and unpack_mask(e_mask, n).all() and not _np(e_cnt).any()
+
+
+def test_packet_stream_end_to_end(codecs):
+    """encode -> packets -> a lossy, reordering network -> reassembly -> decode: the codec behind its front-ends."""
+    from ldpc_erasure_codes_b200.codec import unpack_mask
+    codec = codecs(1, 64)
+    code = orc.Code.builtin(1)
+    B, block0 = 40, 236                                   # wraps past 255
+    info = _rand_info(B, codec.k, 64, seed=77)
+    packets = _np(codec.packetize(codec.encode(info), block0))
+    rng = np.random.default_rng(1)
+    arrived = packets[rng.permutation(len(packets))]
+    arrived = arrived[rng.random(len(arrived)) >= 0.15]   # 15 % packet loss
+    rx, mask, counts = codec.depacketize(torch.from_numpy(arrived).cuda(), block0, B)
+    assert int(_np(counts)[:B].sum()) == len(arrived) and int(_np(counts)[B]) == 0
+    out, fail = codec.decode(rx, mask)
+    flags = unpack_mask(mask, code.n)
+    ref = orc.decode(code, _np(rx), flags, max_iter=50, mode="peel")
+    assert np.array_equal(_np(out), ref["out"]) and np.array_equal(_np(fail), ref["fail_sys"])
+    good = _np(fail) == 0
+    assert good.sum() >= B - 1 and np.array_equal(_np(out)[good], _np(info)[good])
+    n, k = codec.n, codec.k
+    assert codec.ready_to_decode(n, 0) and not codec.ready_to_decode(k + 408, 11) and codec.ready_to_decode(k + 409, 11)
+    assert all(codec.ready_to_decode(c, x) == orc.ready_to_decode(n, k, c, x) for c in range(1500, 2041, 7) for x in (0, 10, 11, 100, 101))
