@@ -1015,7 +1015,7 @@ struct HybridScratch {
     int wpc[3] = {0, 0, 0}, slot_words[3] = {0, 0, 0};
     uint32_t *d_plan = nullptr;          // [max_batch][plan_words] recorded solutions of the inactivation stage
     int plan_words = 0;
-    int wpc_pat = 0, slot_words_pat = 0;                     // stage 0 without payload (error-rate runs): smaller slots
+    int wpc_pat[2] = {0, 0}, slot_words_pat[2] = {0, 0};     // the pattern kernel of stages 0 / 1 (no payload: smaller slots, more warps)
     uint32_t *d_gmat = nullptr;         // per-CTA matrices when they do not fit in shared memory
     int grid = 0, smem = 0, RSW = 0;
     bool ready = false;
@@ -1062,10 +1062,13 @@ inline int hybrid_prepare(HybridScratch &h, const HostCode &code, int S, int NW,
         }
         if (h.slot_words[0] <= fx + 64) h.wpc[0] = 0;
         if (h.wpc[1] >= h.wpc[0] && h.wpc[0] > 0) { h.wpc[0] = h.wpc[1]; h.slot_words[0] = h.slot_words[1]; h.wpc[1] = 0; }   // no need for two sizes
-        const long long sp = fx + ge_inact_area_words(code.m, code.m, code.VW, false);
-        h.wpc_pat = int(std::max<long long>(1, std::min<long long>(16, budget_w / sp)));
-        h.slot_words_pat = int((budget_w / h.wpc_pat) & ~3ll);
-        if (h.wpc[0] == 0 || h.slot_words_pat < sp) h.wpc_pat = 0;
+        for (int i = 0; i < 2; i++) {   // pattern slots: typical for stage 0 when a worst-case stage follows, else worst case
+            const int rows = (i == 0 && h.wpc[1] > 0) ? typ : code.m;
+            const long long sp = fx + ge_inact_area_words(rows, rows, code.VW, false);
+            h.wpc_pat[i] = int(std::max<long long>(1, std::min<long long>(16, budget_w / sp)));
+            h.slot_words_pat[i] = int((budget_w / h.wpc_pat[i]) & ~3ll);
+            if (h.wpc[i] == 0 || h.slot_words_pat[i] < sp) h.wpc_pat[i] = 0;
+        }
         if ((e = cudaFuncSetAttribute(hybrid_ge_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin - 1024)) != cudaSuccess)
             return bad("hybrid: cudaFuncSetAttribute", e);
         if ((e = cudaFuncSetAttribute(hybrid_inact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin - 1024)) != cudaSuccess)
@@ -1073,7 +1076,7 @@ inline int hybrid_prepare(HybridScratch &h, const HostCode &code, int S, int NW,
         if ((e = cudaFuncSetAttribute(hybrid_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin - 1024)) != cudaSuccess)
             return bad("hybrid: cudaFuncSetAttribute", e);
         h.plan_words = ge_plan_layout(code.m, NW, code.VW).words;
-        if (h.wpc[0] > 0 && h.wpc_pat > 0)
+        if (h.wpc[0] > 0 && h.wpc_pat[0] > 0)
             if ((e = cudaMalloc(&h.d_plan, size_t(max_batch) * h.plan_words * 4)) != cudaSuccess) return bad("hybrid: plan buffer", e);
     }
     h.RSW = 2 * MW + 1;

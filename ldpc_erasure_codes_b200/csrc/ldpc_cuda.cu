@@ -755,12 +755,12 @@ static int decode_chunk(ldpc_ctx *c, const uint8_t *d_cw, const uint32_t *d_mask
             wp.list_out = const_cast<unsigned int *>(lists[li + 1]); wp.count_out = c->hyb.d_count + li + 1;
             int wpc = c->hyb.wpc[sg], slot = c->hyb.slot_words[sg];
             wp.plan = nullptr; wp.plan_count = nullptr; wp.plan_words = 0; wp.apply_slot_words = 0;
-            const bool split = sg < 2 && !pattern_only && c->hyb.d_plan && c->hyb.wpc_pat > 0 && ge_split();
-            if (sg == 0 && pattern_only && c->hyb.wpc_pat > 0) { wpc = c->hyb.wpc_pat; slot = c->hyb.slot_words_pat; }
+            const bool split = sg < 2 && !pattern_only && c->hyb.d_plan && c->hyb.wpc_pat[sg] > 0 && ge_split();
+            if (sg < 2 && pattern_only && c->hyb.wpc_pat[sg] > 0) { wpc = c->hyb.wpc_pat[sg]; slot = c->hyb.slot_words_pat[sg]; }
             if (split) {   // pattern part at full occupancy, recording plans; the payload replay follows
                 wp.plan = c->hyb.d_plan; wp.plan_count = c->hyb.d_count + 8 + sg; wp.plan_words = c->hyb.plan_words;
                 wp.apply_slot_words = c->hyb.slot_words[sg];
-                wpc = c->hyb.wpc_pat; slot = c->hyb.slot_words_pat;
+                wpc = c->hyb.wpc_pat[sg]; slot = c->hyb.slot_words_pat[sg];
             }
             wp.work_ctr = c->hyb.d_count + 4 + sg; wp.slot_words = slot;
             const size_t smem = size_t(wpc) * slot * 4;
