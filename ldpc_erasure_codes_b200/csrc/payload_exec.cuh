@@ -265,10 +265,7 @@ payload_exec_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
             return true;
         };
         bool have = next_task();
-        const bool timed = p.phase_cycles != nullptr && wl == 0;
-        long long tk0 = 0, tk_spin = 0, tk_exec = 0, tk_prep = 0;
         while (have) {
-            if (timed) tk0 = clock64();
             if (done_target) {                        // wait for the levels below
                 uint32_t seen, spins = 0;
                 do {
@@ -279,7 +276,6 @@ payload_exec_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
                     }
                 } while (seen < done_target);
             }
-            if (timed) { const long long t = clock64(); tk_spin += t - tk0; tk0 = t; }
             while (t_valid) {
                 uint4 val[RWM];
 #pragma unroll
@@ -296,16 +292,8 @@ payload_exec_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
             __syncwarp();
             if (wl == 0)
                 asm volatile("red.release.cta.shared::cta.add.u32 [%0], %1;" ::"r"(done_a), "r"(1u) : "memory");
-            if (timed) { const long long t = clock64(); tk_exec += t - tk0; tk0 = t; }
             have = next_task();                        // off the critical path: my next level, addresses prepared
-            if (timed) { const long long t = clock64(); tk_prep += t - tk0; }
         }
-        if (timed) {   // [5] spin, [6] gather+store+release, [7] next-task preparation: cycles summed over the group's warps
-            atomicAdd(&p.phase_cycles[5], (unsigned long long)tk_spin);
-            atomicAdd(&p.phase_cycles[6], (unsigned long long)tk_exec);
-            atomicAdd(&p.phase_cycles[7], (unsigned long long)tk_prep);
-        }
-
         // ---- store the first rows_out rows, recycle the slot --------------------------------
         fence_proxy_async_smem();
         named_bar_sync(bar_id, GT);

@@ -35,7 +35,6 @@ for P in rates:
         ph = pr.get("exec_phase_cycles", [0] * 8)
         if ph[4]:
             r["phase_cyc_per_unit"] = dict(claim=ph[0] // ph[4], load=ph[1] // ph[4], xor=ph[2] // ph[4], store=ph[3] // ph[4])
-            r["xor_warp_cyc_per_unit"] = dict(spin=ph[5] // ph[4] // 4, work=ph[6] // ph[4] // 4, prep=ph[7] // ph[4] // 4)
         print(json.dumps(r), flush=True); res.append(r)
 # encode
 for (W, slots) in geoms:
