@@ -5,7 +5,9 @@
 // elimination with row swaps (:57-75) and Jordan back-elimination (:77-86); it aborts when a column
 // has no pivot (:59-62), i.e. exactly when rank(H(:,E)) < |E|.  On success the solution is unique,
 // so ANY exact solver returns the same bytes; on abort the contract (SURVEY a-10) is "leave the
-// peeling result, report ml_fail".  This kernel therefore uses its own GPU-friendly elimination:
+// peeling result, report ml_fail".  Three solvers run back to back, each taking what the previous one
+// deferred: inactivation decoding per warp (hybrid_inact_kernel + hybrid_apply_kernel, below),
+// plain Gauss-Jordan per warp (hybrid_ge_warp_kernel), and the CTA-wide kernel described first:
 //
 //   one CTA per codeword that left the peeling stage with erasures (compacted list from the peel
 //   kernel).  The m x e bit matrix A = H(:,E) is built bit-packed in shared memory next to an
@@ -14,8 +16,8 @@
 //   and XORed -- 32 words per warp instruction -- into every other row that has the bit.  No pivot
 //   => rank deficient => ml_fail.  At the end row pivot(j) of the I part lists which check
 //   syndromes add up to unknown j.  Payload: the syndromes  s_r = XOR of the KNOWN members of check r
-//   (received or peeled; the executor stored all n symbols of such codewords) are formed in shared
-//   memory, 64 bytes of every symbol at a time, and every erased SYSTEMATIC symbol is written as the
+//   (received or peeled; the executor formed them while the codeword was in its shared memory) are
+//   read 64 bytes of every symbol at a time, and every erased SYSTEMATIC symbol is written as the
 //   XOR of its syndromes straight into the decoder output.  There is no dependency chain in the
 //   payload part: all unknowns are independent combinations of the syndromes.
 //
@@ -1027,7 +1029,7 @@ inline void hybrid_free(HybridScratch &h)
     h = HybridScratch();
 }
 
-// Allocates the stage's scratch on first use (the full-codeword buffer is large: max_batch * n * S).
+// Allocates the stage's scratch on first use (syndromes max_batch * m * S, plans max_batch * ~16 KB).
 inline int hybrid_prepare(HybridScratch &h, const HostCode &code, int S, int NW, int MW, int num_sms, int smem_optin,
                           long long max_batch, std::string &err)
 {
