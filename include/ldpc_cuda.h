@@ -149,7 +149,12 @@ int ldpc_gen_erasures(ldpc_ctx *ctx, const ldpc_erasure_model *model, uint32_t s
  * host flag -i, default 50); the decoder reproduces the serial sweep order exactly, so a
  * binding cap gives the reference's partial result.  In LDPC_MODE_HYBRID max_iter is the
  * sweep cap before elimination (10 in the MATLAB file) and d_fail additionally covers
- * rank-deficient eliminations.                                                           */
+ * rank-deficient eliminations.  Erased symbols of d_cw are all-zero by the reference's
+ * convention (ldpc_gen_erasures and ldpc_depacketize leave them so), but no decoder here reads
+ * them: a symbol that stays unknown is passed through to d_out as it came (peel mode) or as
+ * zeros (hybrid mode, frames that reached the elimination stage).  A batch larger than
+ * max_batch is cut into max_batch chunks that alternate between two internal streams; the
+ * caller's stream continues when all of them are done.                                    */
 int ldpc_decode(ldpc_ctx *ctx, const void *d_cw, const uint32_t *d_mask, void *d_out,
                 uint8_t *d_fail, int max_iter, int mode, int64_t B, void *stream);
 
