@@ -18,7 +18,13 @@
  *   - work is enqueued on the caller's stream, no hidden synchronisation
  *     except in the *_host variants and ldpc_get_stats();
  *   - a context is bound to one GPU and is thread-compatible (one context per
- *     GPU per host thread), like the reference's single-threaded host.
+ *     GPU per host thread), like the reference's single-threaded host.  Contexts
+ *     on different GPUs may live in one process and be driven from one thread or
+ *     from one thread each (ldpc_*_host_multi does the latter).  A context's
+ *     scratch (schedules, syndromes) is shared by all its calls: keep ONE
+ *     stream's worth of work in flight per context -- calls on one stream are
+ *     ordered; calls on different streams need the caller's own event between
+ *     them.
  *
  * Data layout (the GPU form of the reference's `symbol_type`,
  * OpenCL/device/ldpc_erasure_decoder_top.cl:38-44 = {ulong symbol[128]; uchar
@@ -39,7 +45,7 @@
 extern "C" {
 #endif
 
-#define LDPC_CUDA_ABI_VERSION 1
+#define LDPC_CUDA_ABI_VERSION 2
 
 enum {
     LDPC_OK = 0,
@@ -100,6 +106,9 @@ typedef struct ldpc_stats {
     int64_t ml_recovered;     /* hybrid mode: frames counted in ldpc_errors whose systematic
                                  symbols the elimination then recovered (hybrid frame errors =
                                  ldpc_errors - ml_recovered)                         */
+    int64_t any_errors;       /* frames with ANY of the n symbols still unknown after decoding:
+                                 the MATLAB harness's block-error criterion
+                                 (LDPCErasureCodes_MessagePassingAlgSim.m:229-236)    */
 } ldpc_stats;
 
 /* ---- context ------------------------------------------------------------------------
@@ -136,7 +145,11 @@ int ldpc_encode(ldpc_ctx *ctx, const void *d_info, void *d_cw, int64_t B, void *
  * Replaces the decoder-side data_in kernel (ldpc_erasure_decoder_top.cl:57-120):
  * Threefry4x32-20, key {1, seed}, counter 1 + (frame0 + b) * n + symbol.  Writes the
  * erasure mask of B codewords and, if d_payload != NULL, zeroes the erased symbols of
- * d_payload [B][n][S] in place (the "erased = all zero" convention).                     */
+ * d_payload [B][n][S] in place (the "erased = all zero" convention).
+ * The counter is 32 bits wide and wraps, as the reference's `c.v[0]++` does: for one seed the
+ * frame sequence repeats after 2^32 / gcd(2^32, n) frames (2^28 = 2.7e8 for n = 2000 and 4000,
+ * 2^29 = 5.4e8 for n = 2040).  Longer runs must change the seed per period (tools/bler_deep.py
+ * does); frame0 + B beyond one period replays frames.                                       */
 int ldpc_gen_erasures(ldpc_ctx *ctx, const ldpc_erasure_model *model, uint32_t seed,
                       uint64_t frame0, int64_t B, uint32_t *d_mask, void *d_payload, void *stream);
 
@@ -157,6 +170,12 @@ int ldpc_gen_erasures(ldpc_ctx *ctx, const ldpc_erasure_model *model, uint32_t s
  * caller's stream continues when all of them are done.                                    */
 int ldpc_decode(ldpc_ctx *ctx, const void *d_cw, const uint32_t *d_mask, void *d_out,
                 uint8_t *d_fail, int max_iter, int mode, int64_t B, void *stream);
+/* The same with the second failure criterion the reference uses: d_fail_any [B] (may be NULL)
+ * receives 1 where ANY of the n symbols is still unknown after decoding -- the MATLAB harness
+ * compares all n symbols with the truth (LDPCErasureCodes_MessagePassingAlgSim.m:229-236), the
+ * OpenCL kernel only the first k (d_fail).  d_fail_any[b] >= d_fail[b].                      */
+int ldpc_decode_ex(ldpc_ctx *ctx, const void *d_cw, const uint32_t *d_mask, void *d_out,
+                   uint8_t *d_fail, uint8_t *d_fail_any, int max_iter, int mode, int64_t B, void *stream);
 
 /* ---- error-rate run ---------------------------------------------------------------
  * The reference's committed flow in one call (main.cpp:555-659 with decoder_top.cl:57-158 and
@@ -207,6 +226,17 @@ int ldpc_profile_read(ldpc_ctx *ctx, ldpc_profile *out, int reset);
 int ldpc_encode_host(ldpc_ctx *ctx, const void *h_info, void *h_cw, int64_t B);
 int ldpc_decode_host(ldpc_ctx *ctx, const void *h_cw, const uint32_t *h_mask, void *h_out,
                      uint8_t *h_fail, int max_iter, int mode, int64_t B);
+int ldpc_decode_host_ex(ldpc_ctx *ctx, const void *h_cw, const uint32_t *h_mask, void *h_out,
+                        uint8_t *h_fail, uint8_t *h_fail_any, int max_iter, int mode, int64_t B);
+/* The whole box: ctxs[n_ctx] = one context per GPU, same code and symbol size.  The
+ * batch is cut into contiguous frame ranges -- GPU g takes frames [g*B/G, (g+1)*B/G) -- and one host
+ * thread per GPU drives that GPU's pipeline; there is no exchange between the GPUs (codewords are
+ * independent, ldpc_erasure_decoder.cl:27-104).  Counters stay per context (sum them with
+ * ldpc_get_stats).  Returns the first failing GPU's code; its message names the GPU.             */
+int ldpc_encode_host_multi(ldpc_ctx *const *ctxs, int n_ctx, const void *h_info, void *h_cw, int64_t B);
+int ldpc_decode_host_multi(ldpc_ctx *const *ctxs, int n_ctx, const void *h_cw, const uint32_t *h_mask,
+                           void *h_out, uint8_t *h_fail, uint8_t *h_fail_any, int max_iter, int mode,
+                           int64_t B);
 
 /* ---- synthetic payload --------------------------------------------------------------
  * Counter-based uniform bytes (Threefry key {2, seed}, counter = 16-byte block index +

@@ -11,8 +11,8 @@ SO_PATH = os.path.join(HERE, "libldpc_cuda.so")
 # every symbol include/ldpc_cuda.h declares (tests check the library exports all of them)
 EXPORTS = [
     "ldpc_ctx_create", "ldpc_ctx_destroy", "ldpc_ctx_info", "ldpc_read_h_file", "ldpc_ctx_get_csr", "ldpc_ctx_set_exec_geometry",
-    "ldpc_encode", "ldpc_gen_erasures", "ldpc_decode", "ldpc_simulate_fer", "ldpc_get_stats", "ldpc_reset_stats",
-    "ldpc_encode_host", "ldpc_decode_host", "ldpc_fill_random", "ldpc_packetize", "ldpc_depacketize", "ldpc_ready_to_decode", "ldpc_profile_enable", "ldpc_profile_read",
+    "ldpc_encode", "ldpc_gen_erasures", "ldpc_decode", "ldpc_decode_ex", "ldpc_simulate_fer", "ldpc_get_stats", "ldpc_reset_stats",
+    "ldpc_encode_host", "ldpc_decode_host", "ldpc_decode_host_ex", "ldpc_encode_host_multi", "ldpc_decode_host_multi", "ldpc_fill_random", "ldpc_packetize", "ldpc_depacketize", "ldpc_ready_to_decode", "ldpc_profile_enable", "ldpc_profile_read",
     "rs_ctx_create", "rs_ctx_destroy", "rs_ctx_get_generator", "rs_encode", "rs_decode",
     "ldpc_last_error_string", "ldpc_cuda_abi_version",
 ]
@@ -36,7 +36,7 @@ class ErasureModel(C.Structure):
 
 
 class Stats(C.Structure):
-    _fields_ = [(n, C.c_int64) for n in ("frames", "ldpc_errors", "rs_errors", "ml_attempts", "ml_failures", "ml_recovered")]
+    _fields_ = [(n, C.c_int64) for n in ("frames", "ldpc_errors", "rs_errors", "ml_attempts", "ml_failures", "ml_recovered", "any_errors")]
 
 
 K_KINDS = 8
@@ -69,11 +69,15 @@ def load():
     lib.ldpc_encode.argtypes = [vp, vp, vp, i64, vp]
     lib.ldpc_gen_erasures.argtypes = [vp, C.POINTER(ErasureModel), u32, u64, i64, vp, vp, vp]
     lib.ldpc_decode.argtypes = [vp, vp, vp, vp, vp, i32, i32, i64, vp]
+    lib.ldpc_decode_ex.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i64, vp]
     lib.ldpc_simulate_fer.argtypes = [vp, C.POINTER(ErasureModel), u32, u64, i64, i32, i32, vp]
     lib.ldpc_get_stats.argtypes = [vp, C.POINTER(Stats)]
     lib.ldpc_reset_stats.argtypes = [vp]
     lib.ldpc_encode_host.argtypes = [vp, vp, vp, i64]
     lib.ldpc_decode_host.argtypes = [vp, vp, vp, vp, vp, i32, i32, i64]
+    lib.ldpc_decode_host_ex.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i64]
+    lib.ldpc_encode_host_multi.argtypes = [C.POINTER(vp), i32, vp, vp, i64]
+    lib.ldpc_decode_host_multi.argtypes = [C.POINTER(vp), i32, vp, vp, vp, vp, vp, i32, i32, i64]
     lib.ldpc_fill_random.argtypes = [vp, i64, u32, u64, i32, vp]
     lib.ldpc_packetize.argtypes = [vp, vp, u32, i64, vp, vp]
     lib.ldpc_depacketize.argtypes = [vp, vp, i64, u32, i64, vp, vp, vp, vp]

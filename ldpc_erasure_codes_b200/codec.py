@@ -117,7 +117,9 @@ class LdpcCodec:
                                               {"peel": MODE_PEEL, "hybrid": MODE_HYBRID}[mode], _stream()))
 
     # ---- ldpc_erasure_decoder(num_iter, code_ind) + data_out ----------------------------
-    def decode(self, cw: torch.Tensor, mask: torch.Tensor, max_iter=50, mode="peel", out=None, fail=None):
+    def decode(self, cw: torch.Tensor, mask: torch.Tensor, max_iter=50, mode="peel", out=None, fail=None, fail_any=None):
+        """-> (out [B][k][S], fail [B]); pass a [B] uint8 tensor as fail_any to also get the MATLAB harness's
+        criterion (any of the n symbols still unknown, LDPCErasureCodes_MessagePassingAlgSim.m:229-236)."""
         assert cw.is_cuda and cw.dtype == torch.uint8 and cw.is_contiguous() and mask.is_contiguous()
         B = cw.shape[0]
         assert cw.shape[1:] == (self.n, self.S) and mask.shape == (B, self.mask_words)
@@ -125,8 +127,8 @@ class LdpcCodec:
             out = torch.empty((B, self.k, self.S), dtype=torch.uint8, device=cw.device)
         if fail is None:
             fail = torch.empty((B,), dtype=torch.uint8, device=cw.device)
-        _lib.check(self.lib.ldpc_decode(self._h, _ptr(cw), _ptr(mask), _ptr(out), _ptr(fail), max_iter,
-                                        {"peel": MODE_PEEL, "hybrid": MODE_HYBRID}[mode], B, _stream()))
+        _lib.check(self.lib.ldpc_decode_ex(self._h, _ptr(cw), _ptr(mask), _ptr(out), _ptr(fail), _ptr(fail_any), max_iter,
+                                           {"peel": MODE_PEEL, "hybrid": MODE_HYBRID}[mode], B, _stream()))
         return out, fail
 
     # ---- FEC packet front-ends (encoder_VITA_in_UDP_out.cl / decoder_with_reordering_logic.cl) ----
@@ -193,6 +195,33 @@ class LdpcCodec:
         d["ge_phase_cycles"] = list(p.ge_phase_cycles)
         d["apply_phase_cycles"] = list(p.apply_phase_cycles)
         return d
+
+
+def decode_host_multi(codecs, cw: torch.Tensor, mask: torch.Tensor, max_iter=50, mode="peel", out=None, fail=None, fail_any=None):
+    """One host batch over several GPUs (ldpc_decode_host_multi): codecs = one LdpcCodec per device, same code and S;
+    cw / mask are HOST tensors; frames [g*B/G, (g+1)*B/G) go to GPU g, one host thread per GPU inside the library."""
+    c0 = codecs[0]
+    assert not cw.is_cuda and cw.dtype == torch.uint8 and cw.is_contiguous()
+    B = cw.shape[0]
+    if out is None:
+        out = torch.empty((B, c0.k, c0.S), dtype=torch.uint8, pin_memory=True)
+    if fail is None:
+        fail = torch.empty((B,), dtype=torch.uint8, pin_memory=True)
+    arr = (C.c_void_p * len(codecs))(*[c._h for c in codecs])
+    _lib.check(c0.lib.ldpc_decode_host_multi(arr, len(codecs), _ptr(cw), _ptr(mask), _ptr(out), _ptr(fail), _ptr(fail_any), max_iter,
+                                             {"peel": MODE_PEEL, "hybrid": MODE_HYBRID}[mode], B))
+    return out, fail
+
+
+def encode_host_multi(codecs, info: torch.Tensor, out=None):
+    c0 = codecs[0]
+    assert not info.is_cuda and info.dtype == torch.uint8 and info.is_contiguous()
+    B = info.shape[0]
+    if out is None:
+        out = torch.empty((B, c0.n, c0.S), dtype=torch.uint8, pin_memory=True)
+    arr = (C.c_void_p * len(codecs))(*[c._h for c in codecs])
+    _lib.check(c0.lib.ldpc_encode_host_multi(arr, len(codecs), _ptr(info), _ptr(out), B))
+    return out
 
 
 def read_h_file(path: str):

@@ -253,8 +253,8 @@ int build_code(int rows, int cols, const std::vector<int32_t> &col_ptr,
         code.max_row_weight = std::max(code.max_row_weight, w);
         if (w == 0 || code.col_idx[code.row_ptr[r + 1] - 1] != code.k + r) code.triangular = false;
     }
-    if (code.n > 65534 || code.m > 2047 || code.max_row_weight > 31) {
-        err = "code outside kernel limits (n <= 65534, m <= 2047, row weight <= 31)";
+    if (code.n > 65534 || code.m > 2047 || code.max_row_weight > 30) {   // (the peel kernel's 5-bit erased-member count keeps 31 as its "fired" mark)
+        err = "code outside kernel limits (n <= 65534, m <= 2047, row weight <= 30)";
         return LDPC_ERR_UNSUPPORTED;
     }
     code.RW = (code.max_row_weight + 7) & ~7;
@@ -263,7 +263,7 @@ int build_code(int rows, int cols, const std::vector<int32_t> &col_ptr,
     for (int r = 0; r < rows; r++)
         for (int j = code.row_ptr[r]; j < code.row_ptr[r + 1]; j++)
             code.cidx[size_t(r) * code.RW + (j - code.row_ptr[r])] = uint16_t(code.col_idx[j]);
-    code.vadj.assign(size_t(cols) * code.VW, 0xFFFFu);
+    code.vadj.assign((size_t(cols) * code.VW + 7) & ~size_t(7), 0xFFFFu);   // padded to 16 bytes: the kernels stage it with 128-bit copies
     for (int c = 0; c < cols; c++)
         for (int j = col_ptr[c]; j < col_ptr[c + 1]; j++)
             code.vadj[size_t(c) * code.VW + (j - col_ptr[c])] = uint16_t(row_idx[j]);

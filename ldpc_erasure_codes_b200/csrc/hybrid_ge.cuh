@@ -43,6 +43,7 @@ struct GeParams {
                                      // valid for listed codewords), or nullptr = error-rate run, pattern only
     uint8_t *out;                    // [B][k][S]
     uint8_t *fail;                   // [B]
+    uint8_t *fail_any;               // [B] or nullptr: cleared when the elimination succeeds (all n symbols are then known)
     unsigned long long *stats;       // [3] ml_attempts, [4] ml_failures, [5] ml_recovered
     const uint16_t *cidx;            // [m][RW]
     const uint16_t *vadj;            // [n][VW] variable -> checks
@@ -223,6 +224,7 @@ __global__ void __launch_bounds__(kGeThreads) hybrid_ge_kernel(const GeParams p)
             atomicAdd(&p.stats[3], 1ull);
             if (ok) {
                 if (p.fail) p.fail[cw] = 0;
+                if (p.fail_any) p.fail_any[cw] = 0;
                 if (hdr[3] != 0u) atomicAdd(&p.stats[5], 1ull);   // a frame the peel kernel counted as an error
             } else {
                 atomicAdd(&p.stats[4], 1ull);
@@ -472,6 +474,7 @@ __global__ void __launch_bounds__(512) hybrid_ge_warp_kernel(const GeWarpParams 
             atomicAdd(&p.stats[3], 1ull);
             if (ok) {
                 if (p.fail) p.fail[cw] = 0;
+                if (p.fail_any) p.fail_any[cw] = 0;
                 if (hdr[3] != 0u) atomicAdd(&p.stats[5], 1ull);   // a frame the peel kernel counted as an error
             } else {
                 atomicAdd(&p.stats[4], 1ull);
@@ -826,6 +829,7 @@ __global__ void __launch_bounds__(512) hybrid_inact_kernel(const GeWarpParams q)
             atomicAdd(&p.stats[3], 1ull);
             if (ok) {
                 if (p.fail) p.fail[cw] = 0;
+                if (p.fail_any) p.fail_any[cw] = 0;
                 if (hdr[3] != 0u) atomicAdd(&p.stats[5], 1ull);   // a frame the peel kernel counted as an error
             } else {
                 atomicAdd(&p.stats[4], 1ull);
@@ -1034,8 +1038,9 @@ inline int hybrid_prepare(HybridScratch &h, const HostCode &code, int S, int NW,
                           long long max_batch, std::string &err)
 {
     if (h.ready) return LDPC_OK;
-    auto bad = [&](const char *what, cudaError_t e) {
+    auto bad = [&](const char *what, cudaError_t e) {   // a failed set-up leaves nothing allocated: a retry starts clean
         err = std::string(what) + ": " + cudaGetErrorString(e);
+        hybrid_free(h);
         return e == cudaErrorMemoryAllocation ? LDPC_ERR_NOMEM : LDPC_ERR_CUDA;
     };
     cudaError_t e;
@@ -1085,7 +1090,7 @@ inline int hybrid_prepare(HybridScratch &h, const HostCode &code, int S, int NW,
     const size_t base = size_t(code.m) * 64 + ge_small_bytes(code.m, NW) + 16;
     const size_t mat = size_t(code.m) * h.RSW * 4;
     const size_t budget = size_t(smem_optin) - 1024;
-    if (base > budget) { err = "hybrid: code too large for the elimination kernel"; return LDPC_ERR_UNSUPPORTED; }
+    if (base > budget) { err = "hybrid: code too large for the elimination kernel"; hybrid_free(h); return LDPC_ERR_UNSUPPORTED; }
     if (base + mat <= budget) {
         h.smem = int(base + mat);
         h.grid = num_sms * int(std::max<size_t>(1, std::min<size_t>(2, budget / (base + mat))));

@@ -11,7 +11,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
+#include <mutex>
 #include <string>
+#include <thread>
+#include <utility>
 #include <vector>
 
 #include "../../include/ldpc_cuda.h"
@@ -43,16 +47,21 @@ static int fail(int code, const std::string &msg)
             return fail(LDPC_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));  \
     } while (0)
 
-// cudaFuncAttributeMaxDynamicSharedMemorySize is per-function process state: raise it once to the
-// device maximum (minus the kernel's static shared memory) instead of per-context values
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) applies to the CURRENT device's copy of the function: it is raised
+// once per (device, function) to the device maximum minus the kernel's static shared memory.  Contexts on different
+// GPUs may be created and used from different host threads, so the record is locked.
 static int allow_max_smem(const void *func, int smem_optin)
 {
-    static std::vector<const void *> done;
-    for (const void *f : done) if (f == func) return LDPC_OK;
+    static std::mutex mu;
+    static std::vector<std::pair<int, const void *>> done;
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    for (const auto &d : done) if (d.first == dev && d.second == func) return LDPC_OK;
     cudaFuncAttributes a;
     CUDA_TRY(cudaFuncGetAttributes(&a, func));
     CUDA_TRY(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin - int(a.sharedSizeBytes)));
-    done.push_back(func);
+    done.emplace_back(dev, func);
     return LDPC_OK;
 }
 
@@ -65,11 +74,18 @@ static int ge_stage_mask() { const char *e = getenv("LDPC_CUDA_GE_STAGES"); retu
 // LDPC_CUDA_TMA4=0: the executor moves its slots box by box (3-D tensor copies only)
 static const bool g_tma4 = [] { const char *e = getenv("LDPC_CUDA_TMA4"); return !(e && *e == '0'); }();
 
+// LDPC_CUDA_EXEC_WIDE_MIN: executor levels with more entries than this are spread over a group's four warps (default:
+// what one warp covers in one pass); smaller levels are walked by one warp alone
+static int exec_wide_min(int entries_per_warp_pass)
+{
+    static const int forced = [] { const char *e = getenv("LDPC_CUDA_EXEC_WIDE_MIN"); return e && *e ? atoi(e) : -1; }();
+    return forced >= 0 ? forced : entries_per_warp_pass;
+}
+
 // LDPC_CUDA_DEBUG_SYNC=1: synchronise after every launch so that a faulting kernel is named
 static int debug_sync(const char *what, cudaStream_t st)
 {
-    static int on = -1;
-    if (on < 0) { const char *e = getenv("LDPC_CUDA_DEBUG_SYNC"); on = (e && *e && *e != '0') ? 1 : 0; }
+    static const bool on = [] { const char *e = getenv("LDPC_CUDA_DEBUG_SYNC"); return e && *e && *e != '0'; }();
     if (!on) return LDPC_OK;
     cudaError_t e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return fail(LDPC_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
@@ -90,14 +106,13 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32
 
 static int get_encode_fn(PFN_encodeTiled *fn)
 {
-    static PFN_encodeTiled cached = nullptr;
-    if (!cached) {
+    static const PFN_encodeTiled cached = [] {      // (initialised once, thread-safe)
         void *p = nullptr;
         cudaDriverEntryPointQueryResult q;
-        CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
-        if (!p || q != cudaDriverEntryPointSuccess) return fail(LDPC_ERR_CUDA, "cuTensorMapEncodeTiled not available");
-        cached = reinterpret_cast<PFN_encodeTiled>(p);
-    }
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+        return reinterpret_cast<PFN_encodeTiled>(p);
+    }();
+    if (!cached) return fail(LDPC_ERR_CUDA, "cuTensorMapEncodeTiled not available");
     *fn = cached;
     return LDPC_OK;
 }
@@ -140,6 +155,9 @@ static int make_map4(CUtensorMap *map, const void *base, int S, int rows, long l
     return LDPC_OK;
 }
 
+struct ldpc_ctx;
+static int cached_map(ldpc_ctx *c, CUtensorMap *out, const void *base, int rows, long long B, int W, int nfull, bool is_load);
+
 // ------------------------------------------------------------------------------------------
 // context
 // ------------------------------------------------------------------------------------------
@@ -163,6 +181,7 @@ struct ldpc_ctx {
     uint32_t *d_resid = nullptr;
     uint8_t *d_fail_scratch = nullptr;
     unsigned long long *d_stats = nullptr;
+    long long hybrid_batch = 0;              // codewords per hybrid-mode chunk (bounds the syndrome scratch)
     unsigned long long *d_phase = nullptr;   // LDPC_CUDA_PHASE_TIMING=1
     uint32_t *d_sim_mask = nullptr;          // ldpc_simulate_fer: masks of one chunk
     unsigned int *d_work_ctr = nullptr;      // peel kernel's codeword claim counter
@@ -184,6 +203,13 @@ struct ldpc_ctx {
     uint32_t *h_mask[2] = {nullptr, nullptr};
     uint8_t *h_fail[2] = {nullptr, nullptr};
     long long host_chunk = 0;
+    bool host_ready = false;
+    uint8_t *h_fail_any[2] = {nullptr, nullptr};
+    cudaEvent_t h_ev = nullptr;              // orders the kernels of consecutive host-pipeline stages (they share the scratch)
+    // tensor maps of recent executor launches (cuTensorMapEncodeTiled is a driver call on the small-batch latency path)
+    struct MapKey { const void *base; int rows, W, nfull, is_load; long long B; };
+    struct MapRec { MapKey key; CUtensorMap map; };
+    std::vector<MapRec> map_cache;
     // profiling
     bool prof_on = false;
     struct ProfRec { cudaEvent_t a, b; int kind; };
@@ -204,6 +230,24 @@ struct ProfScope {
         if (a && b) { cudaEventRecord(b, st); c->prof_recs.push_back({a, b, kind}); }
     }
 };
+
+// nfull == 0: the 3-D map; else the 4-D map over whole boxes
+static int cached_map(ldpc_ctx *c, CUtensorMap *out, const void *base, int rows, long long B, int W, int nfull, bool is_load)
+{
+    for (const auto &r : c->map_cache)
+        if (r.key.base == base && r.key.rows == rows && r.key.B == B && r.key.W == W && r.key.nfull == nfull && r.key.is_load == int(is_load)) {
+            *out = r.map;
+            return LDPC_OK;
+        }
+    ldpc_ctx::MapRec rec;
+    rec.key = {base, rows, W, nfull, int(is_load), B};
+    int rc = nfull ? make_map4(&rec.map, base, c->S, rows, B, W, nfull, is_load) : make_map(&rec.map, base, c->S, rows, B, W, is_load);
+    if (rc) return rc;
+    if (c->map_cache.size() >= 64) c->map_cache.erase(c->map_cache.begin());
+    c->map_cache.push_back(rec);
+    *out = rec.map;
+    return LDPC_OK;
+}
 
 static const struct { const char *name; int n, k, rs_n, rs_k; } kBuiltin[] = {
     // OpenCL/device/LDPC_Vlist_data.h:10-14 (ldpc_params) + the .mat-only (4000,2000) code
@@ -230,12 +274,13 @@ static int choose_geom(const ldpc_ctx *c, bool dynamic_sched, ExecGeom *g)
     const int cidx_bytes = c->code.m * c->code.RW * 2;
     const int blob = sched_blob_max_bytes(c->code.m);
     const int mask_bytes = dynamic_sched ? kExecMaxGroups * ((c->NW + 3) & ~3) * 4 : 0;   // hybrid mode: one mask per slot
-    const int fixed = cidx_bytes + 128 + 128 + 64 + 128 + 128 + mask_bytes;
+    const int fixed = cidx_bytes + 64 + 64 + mask_bytes + 1024;   // check rows, barriers, mailboxes, masks, base alignment
     ExecGeom best;
     for (int W = 64; W >= 16; W >>= 1) {         // instantiated slice widths; S is a multiple of 16, so 16 always divides
         if (W > S || S % W) continue;
         if (c->force_W && W != c->force_W) continue;
-        const int slot = ((n + kBoxRows - 1) / kBoxRows) * kBoxRows * W;
+        const int slot = ((n + kBoxRows - 1) / kBoxRows) * kBoxRows * W + kExecZeroRowBytes;
+        if ((slot - kExecZeroRowBytes) / 16 > 0xFFFF) continue;   // check rows are staged as 16-bit offsets in 16-byte units
         int nslot;
         if (dynamic_sched) nslot = (c->smem_optin - fixed) / (slot + blob);
         else nslot = (c->smem_optin - fixed - blob) / slot;
@@ -244,7 +289,7 @@ static int choose_geom(const ldpc_ctx *c, bool dynamic_sched, ExecGeom *g)
         if (nslot < 1) continue;
         ExecGeom cand;
         cand.W = W; cand.nslot = nslot; cand.slot_bytes = slot; cand.sched_area = blob;
-        cand.smem_bytes = nslot * slot + (dynamic_sched ? nslot : 1) * blob + cidx_bytes + 128 + 128 + 64 + 128 + mask_bytes;
+        cand.smem_bytes = nslot * slot + (dynamic_sched ? nslot : 1) * blob + cidx_bytes + 64 + 64 + mask_bytes;
         if (!best.W || (best.nslot < 3 && cand.nslot > best.nslot)) best = cand;
         if (best.nslot >= 3) break;
     }
@@ -252,6 +297,8 @@ static int choose_geom(const ldpc_ctx *c, bool dynamic_sched, ExecGeom *g)
     *g = best;
     return LDPC_OK;
 }
+
+static void free_host_pipeline(ldpc_ctx *c);
 
 static void free_ctx(ldpc_ctx *c)
 {
@@ -268,10 +315,7 @@ static void free_ctx(ldpc_ctx *c)
     cudaFree(c->d_sched_len); cudaFree(c->d_resid); cudaFree(c->d_stats); cudaFree(c->d_fail_scratch); cudaFree(c->d_phase); cudaFree(c->d_sim_mask);
     hybrid_free(c->hyb);
     for (auto &r : c->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
-    for (int i = 0; i < 2; i++) {
-        if (c->hstream[i]) cudaStreamDestroy(c->hstream[i]);
-        cudaFree(c->h_in[i]); cudaFree(c->h_out[i]); cudaFree(c->h_mask[i]); cudaFree(c->h_fail[i]);
-    }
+    free_host_pipeline(c);
     delete c;
 }
 
@@ -289,7 +333,7 @@ static int setup_peel(ldpc_ctx *c)
 {
     if (c->MW > 64 || (c->code.VW != 4 && c->code.VW != 8))
         return fail(LDPC_ERR_UNSUPPORTED, "peel kernel supports m <= 2048 and column weight <= 8");
-    const int tables = c->code.n * c->code.VW * 2 + c->code.m * c->code.RW * 2;
+    const int tables = ((c->code.n * c->code.VW + 7) & ~7) * 2 + c->code.m * c->code.RW * 2;
     const int per_group = peel_group_words(c->code.m, c->MW, c->NW) * 4;
     const int G = kPeelG;
     int groups = (c->smem_optin - 2048 - tables) / per_group;   // 2 KB margin: static + reserved shared memory
@@ -341,6 +385,8 @@ extern "C" int ldpc_ctx_create(ldpc_ctx **out, const char *h_mat_path, int code_
     c->rs_n = rs_n; c->rs_k = rs_k; c->max_batch = max_batch;
     c->NW = (c->code.n + 31) / 32; c->MW = (c->code.m + 31) / 32;
     c->sched_stride = sched_blob_max_bytes(c->code.m);
+    // hybrid mode keeps one syndrome set (m * S bytes) per codeword of a chunk: chunks are capped so that it stays <= 4 GiB
+    c->hybrid_batch = std::max<long long>(256, std::min<long long>(max_batch, (4ll << 30) / (size_t(c->code.m) * symbol_bytes)));
 
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) { delete c; return fail(LDPC_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e)); }
@@ -486,20 +532,21 @@ static int launch_exec(ldpc_ctx *c, const ExecGeom &g, const void *d_in, int row
 {
     if (B <= 0) return LDPC_OK;
     CUtensorMap in_map, out_map, in4_map, out4_map;
-    int rc = make_map(&in_map, d_in, c->S, rows_in, B, g.W, true);
+    int rc = cached_map(c, &in_map, d_in, rows_in, B, g.W, 0, true);
     if (rc) return rc;
-    rc = make_map(&out_map, d_out, c->S, rows_out, B, g.W, false);
+    rc = cached_map(c, &out_map, d_out, rows_out, B, g.W, 0, false);
     if (rc) return rc;
     const int nfull_in = g_tma4 ? rows_in / kBoxRows : 0, nfull_out = g_tma4 ? rows_out / kBoxRows : 0;
     in4_map = in_map; out4_map = out_map;      // (placeholders when there is no whole box)
-    if (nfull_in) { rc = make_map4(&in4_map, d_in, c->S, rows_in, B, g.W, nfull_in, true); if (rc) return rc; }
-    if (nfull_out) { rc = make_map4(&out4_map, d_out, c->S, rows_out, B, g.W, nfull_out, false); if (rc) return rc; }
+    if (nfull_in) { rc = cached_map(c, &in4_map, d_in, rows_in, B, g.W, nfull_in, true); if (rc) return rc; }
+    if (nfull_out) { rc = cached_map(c, &out4_map, d_out, rows_out, B, g.W, nfull_out, false); if (rc) return rc; }
     ExecParams p;
     p.synd = d_synd; p.mask = d_mask; p.NW = c->NW; p.nfull_in = nfull_in; p.nfull_out = nfull_out;
     p.cidx = c->d_cidx; p.sched = sched; p.sched_len = sched_len; p.B = B; p.sched_stride = sched_stride;
     p.sched_max = g.sched_area; p.m = c->code.m; p.RW = c->code.RW; p.rows_in = rows_in; p.rows_out = rows_out;
     p.nbox_in = (rows_in + kBoxRows - 1) / kBoxRows; p.nbox_out = (rows_out + kBoxRows - 1) / kBoxRows;
     p.slices = c->S / g.W; p.nslot = g.nslot; p.slot_bytes = g.slot_bytes;
+    p.wide_min = exec_wide_min(32 / (g.W / 16));
     p.phase_cycles = sched_stride ? c->d_phase : nullptr;
     int rwm = 0;
     ExecKernel k = pick_exec(g.W, c->code.max_row_weight, &rwm);
@@ -687,23 +734,33 @@ static bool chunk_pipeline() { const char *e = getenv("LDPC_CUDA_CHUNK_PIPELINE"
 
 static int ensure_chunk_pipeline(ldpc_ctx *c)
 {
-    if (c->pstream[0]) return LDPC_OK;
-    CUDA_TRY(cudaMalloc(&c->d_sched2, size_t(c->max_batch) * c->sched_stride));
-    CUDA_TRY(cudaMalloc(&c->d_sched_len2, size_t(c->max_batch) * 4));
-    CUDA_TRY(cudaMalloc(&c->d_resid2, size_t(c->max_batch) * 4));
-    CUDA_TRY(cudaMalloc(&c->d_fail_scratch2, size_t(c->max_batch)));
-    CUDA_TRY(cudaMalloc(&c->d_work_ctr2, sizeof(unsigned int)));
-    for (int i = 0; i < 2; i++) CUDA_TRY(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
-    CUDA_TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
-    CUDA_TRY(cudaStreamCreateWithFlags(&c->pstream[1], cudaStreamNonBlocking));
-    CUDA_TRY(cudaStreamCreateWithFlags(&c->pstream[0], cudaStreamNonBlocking));
-    return LDPC_OK;
+    if (c->pstream[0]) return LDPC_OK;      // (set last: everything below exists)
+    cudaError_t e = cudaSuccess;
+    auto ok = [&](cudaError_t r) { if (e == cudaSuccess) e = r; return e == cudaSuccess; };
+    cudaStream_t s1 = nullptr, s0 = nullptr;
+    if (ok(cudaMalloc(&c->d_sched2, size_t(c->max_batch) * c->sched_stride)) && ok(cudaMalloc(&c->d_sched_len2, size_t(c->max_batch) * 4)) &&
+        ok(cudaMalloc(&c->d_resid2, size_t(c->max_batch) * 4)) && ok(cudaMalloc(&c->d_fail_scratch2, size_t(c->max_batch))) &&
+        ok(cudaMalloc(&c->d_work_ctr2, sizeof(unsigned int))) && ok(cudaEventCreateWithFlags(&c->ev_join[0], cudaEventDisableTiming)) &&
+        ok(cudaEventCreateWithFlags(&c->ev_join[1], cudaEventDisableTiming)) && ok(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming)) &&
+        ok(cudaStreamCreateWithFlags(&s1, cudaStreamNonBlocking)) && ok(cudaStreamCreateWithFlags(&s0, cudaStreamNonBlocking))) {
+        c->pstream[1] = s1;
+        c->pstream[0] = s0;
+        return LDPC_OK;
+    }
+    // a failed set-up leaves nothing behind: the next call starts clean
+    cudaFree(c->d_sched2); cudaFree(c->d_sched_len2); cudaFree(c->d_resid2); cudaFree(c->d_fail_scratch2); cudaFree(c->d_work_ctr2);
+    c->d_sched2 = nullptr; c->d_sched_len2 = nullptr; c->d_resid2 = nullptr; c->d_fail_scratch2 = nullptr; c->d_work_ctr2 = nullptr;
+    for (int i = 0; i < 2; i++) if (c->ev_join[i]) { cudaEventDestroy(c->ev_join[i]); c->ev_join[i] = nullptr; }
+    if (c->ev_fork) { cudaEventDestroy(c->ev_fork); c->ev_fork = nullptr; }
+    if (s1) cudaStreamDestroy(s1);
+    if (s0) cudaStreamDestroy(s0);
+    return fail(e == cudaErrorMemoryAllocation ? LDPC_ERR_NOMEM : LDPC_ERR_CUDA, std::string("chunk pipeline set-up: ") + cudaGetErrorString(e));
 }
 
 // One peel -> executor (-> elimination) pass over B <= max_batch codewords.  (Cutting a batch into pieces
 // on two internal streams so that one piece's executor overlaps the next one's schedule compiler was
 // measured and is no faster: both kernels fill an SM's shared memory and cannot share one.)
-static int decode_chunk(ldpc_ctx *c, const uint8_t *d_cw, const uint32_t *d_mask, uint8_t *d_out, uint8_t *d_fail,
+static int decode_chunk(ldpc_ctx *c, const uint8_t *d_cw, const uint32_t *d_mask, uint8_t *d_out, uint8_t *d_fail, uint8_t *d_fail_any,
                         int max_iter, int mode, long long B, cudaStream_t st, int set = 0)
 {
     uint8_t *const sched = set ? c->d_sched2 : c->d_sched;
@@ -712,13 +769,14 @@ static int decode_chunk(ldpc_ctx *c, const uint8_t *d_cw, const uint32_t *d_mask
     pp.mask = d_mask; pp.sched = sched; pp.sched_len = sched_len;
     pp.work_ctr = set ? c->d_work_ctr2 : c->d_work_ctr;
     pp.fail = d_fail ? d_fail : (set ? c->d_fail_scratch2 : c->d_fail_scratch); pp.resid = set ? c->d_resid2 : c->d_resid; pp.stats = c->d_stats;
+    pp.fail_any = d_fail_any;
     pp.cidx = c->d_cidx; pp.vadj = c->d_vadj; pp.B = B; pp.n = c->code.n; pp.k = c->code.k; pp.m = c->code.m;
     pp.RW = c->code.RW; pp.VW = c->code.VW; pp.NW = c->NW; pp.MW = c->MW; pp.stride = c->sched_stride;
     pp.max_iter = max_iter; pp.rs_n = c->rs_n; pp.rs_k = c->rs_k; pp.groups_per_block = c->peel_groups;
     pp.count_stats = 1;
     pp.ge_list = nullptr; pp.ge_count = nullptr;
     if (mode == LDPC_MODE_HYBRID) {
-        int rch = hybrid_prepare(c->hyb, c->code, c->S, c->NW, c->MW, c->num_sms, c->smem_optin, c->max_batch, g_err);
+        int rch = hybrid_prepare(c->hyb, c->code, c->S, c->NW, c->MW, c->num_sms, c->smem_optin, c->hybrid_batch, g_err);
         if (rch) return rch;
         CUDA_TRY(cudaMemsetAsync(c->hyb.d_count, 0, 16 * 4, st));
         pp.ge_list = c->hyb.d_list; pp.ge_count = c->hyb.d_count;
@@ -740,7 +798,7 @@ static int decode_chunk(ldpc_ctx *c, const uint8_t *d_cw, const uint32_t *d_mask
     if (mode == LDPC_MODE_HYBRID) {
         GeParams gp;
         gp.mask = d_mask; gp.sched = sched; gp.list = c->hyb.d_list; gp.list_count = c->hyb.d_count;
-        gp.synd = pattern_only ? nullptr : c->hyb.d_synd; gp.out = d_out; gp.fail = pp.fail; gp.stats = c->d_stats; gp.cidx = c->d_cidx;
+        gp.synd = pattern_only ? nullptr : c->hyb.d_synd; gp.out = d_out; gp.fail = pp.fail; gp.fail_any = d_fail_any; gp.stats = c->d_stats; gp.cidx = c->d_cidx;
         gp.vadj = c->d_vadj; gp.VW = c->code.VW; gp.phase_cycles = c->d_phase ? c->d_phase + 8 : nullptr; gp.gmat = c->hyb.d_gmat; gp.n = c->code.n; gp.k = c->code.k; gp.m = c->code.m; gp.RW = c->code.RW; gp.NW = c->NW;
         gp.MW = c->MW; gp.S = c->S; gp.stride = c->sched_stride; gp.RSW = c->hyb.RSW;
         // warp-per-codeword stages first (inactivation decoding with typical, then worst-case slots; then plain
@@ -790,8 +848,8 @@ static int decode_chunk(ldpc_ctx *c, const uint8_t *d_cw, const uint32_t *d_mask
     return LDPC_OK;
 }
 
-extern "C" int ldpc_decode(ldpc_ctx *c, const void *d_cw, const uint32_t *d_mask, void *d_out, uint8_t *d_fail,
-                           int max_iter, int mode, int64_t B, void *stream)
+extern "C" int ldpc_decode_ex(ldpc_ctx *c, const void *d_cw, const uint32_t *d_mask, void *d_out, uint8_t *d_fail,
+                              uint8_t *d_fail_any, int max_iter, int mode, int64_t B, void *stream)
 {
     if (!c || B < 0) return fail(LDPC_ERR_ARG, "bad argument to ldpc_decode");
     if (B == 0) return LDPC_OK;
@@ -803,7 +861,8 @@ extern "C" int ldpc_decode(ldpc_ctx *c, const void *d_cw, const uint32_t *d_mask
     const uint8_t *cw = static_cast<const uint8_t *>(d_cw);
     uint8_t *out = static_cast<uint8_t *>(d_out);
     const size_t in_cw = size_t(c->code.n) * c->S, out_cw = size_t(c->code.k) * c->S;
-    const bool pipe = mode == LDPC_MODE_PEEL && !c->prof_on && B > c->max_batch && chunk_pipeline();
+    const long long chunk = mode == LDPC_MODE_HYBRID ? c->hybrid_batch : c->max_batch;
+    const bool pipe = mode == LDPC_MODE_PEEL && !c->prof_on && B > chunk && chunk_pipeline();
     if (pipe) {
         int rc = ensure_chunk_pipeline(c);
         if (rc) return rc;
@@ -811,10 +870,11 @@ extern "C" int ldpc_decode(ldpc_ctx *c, const void *d_cw, const uint32_t *d_mask
         for (int i = 0; i < 2; i++) CUDA_TRY(cudaStreamWaitEvent(c->pstream[i], c->ev_fork, 0));
     }
     int idx = 0;
-    for (long long b0 = 0; b0 < B; b0 += c->max_batch, idx++) {
-        const long long nb = std::min<long long>(c->max_batch, B - b0);
+    for (long long b0 = 0; b0 < B; b0 += chunk, idx++) {
+        const long long nb = std::min<long long>(chunk, B - b0);
         int rc = decode_chunk(c, cw + size_t(b0) * in_cw, d_mask + size_t(b0) * c->NW, out + size_t(b0) * out_cw,
-                              d_fail ? d_fail + b0 : nullptr, max_iter, mode, nb, pipe ? c->pstream[idx & 1] : st, pipe ? (idx & 1) : 0);
+                              d_fail ? d_fail + b0 : nullptr, d_fail_any ? d_fail_any + b0 : nullptr, max_iter, mode, nb,
+                              pipe ? c->pstream[idx & 1] : st, pipe ? (idx & 1) : 0);
         if (rc) return rc;
     }
     if (pipe)
@@ -823,6 +883,12 @@ extern "C" int ldpc_decode(ldpc_ctx *c, const void *d_cw, const uint32_t *d_mask
             CUDA_TRY(cudaStreamWaitEvent(st, c->ev_join[i], 0));
         }
     return LDPC_OK;
+}
+
+extern "C" int ldpc_decode(ldpc_ctx *c, const void *d_cw, const uint32_t *d_mask, void *d_out, uint8_t *d_fail,
+                           int max_iter, int mode, int64_t B, void *stream)
+{
+    return ldpc_decode_ex(c, d_cw, d_mask, d_out, d_fail, nullptr, max_iter, mode, B, stream);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -837,11 +903,12 @@ extern "C" int ldpc_simulate_fer(ldpc_ctx *c, const ldpc_erasure_model *model, u
     CUDA_TRY(cudaSetDevice(c->device));
     if (!c->d_sim_mask) CUDA_TRY(cudaMalloc(&c->d_sim_mask, size_t(c->max_batch) * c->NW * 4));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    for (long long b0 = 0; b0 < frames; b0 += c->max_batch) {
-        const long long nb = std::min<long long>(c->max_batch, frames - b0);
+    const long long sim_chunk = mode == LDPC_MODE_HYBRID ? c->hybrid_batch : c->max_batch;
+    for (long long b0 = 0; b0 < frames; b0 += sim_chunk) {
+        const long long nb = std::min<long long>(sim_chunk, frames - b0);
         int rc = ldpc_gen_erasures(c, model, seed, frame0 + uint64_t(b0), nb, c->d_sim_mask, nullptr, stream);
         if (rc) return rc;
-        rc = decode_chunk(c, nullptr, c->d_sim_mask, nullptr, nullptr, max_iter, mode, nb, st);
+        rc = decode_chunk(c, nullptr, c->d_sim_mask, nullptr, nullptr, nullptr, max_iter, mode, nb, st);
         if (rc) return rc;
     }
     return LDPC_OK;
@@ -859,6 +926,7 @@ extern "C" int ldpc_get_stats(ldpc_ctx *c, ldpc_stats *out)
     CUDA_TRY(cudaMemcpy(h, c->d_stats, sizeof(h), cudaMemcpyDeviceToHost));
     out->frames = (int64_t)h[0]; out->ldpc_errors = (int64_t)h[1]; out->rs_errors = (int64_t)h[2];
     out->ml_attempts = (int64_t)h[3]; out->ml_failures = (int64_t)h[4]; out->ml_recovered = (int64_t)h[5];
+    out->any_errors = (int64_t)h[6] - ((int64_t)h[3] - (int64_t)h[4]);   // unknown after peeling, minus the successful eliminations
     return LDPC_OK;
 }
 
@@ -910,21 +978,41 @@ extern "C" int ldpc_profile_read(ldpc_ctx *c, ldpc_profile *out, int reset)
 // host-buffer entry points: chunked, double-buffered over two streams so that the copy of
 // chunk i+1 overlaps the kernels and the read-back of chunk i.
 // ------------------------------------------------------------------------------------------
+static void free_host_pipeline(ldpc_ctx *c)
+{
+    for (int i = 0; i < 2; i++) {
+        if (c->hstream[i]) { cudaStreamDestroy(c->hstream[i]); c->hstream[i] = nullptr; }
+        cudaFree(c->h_in[i]); cudaFree(c->h_out[i]); cudaFree(c->h_mask[i]); cudaFree(c->h_fail[i]); cudaFree(c->h_fail_any[i]);
+        c->h_in[i] = nullptr; c->h_out[i] = nullptr; c->h_mask[i] = nullptr; c->h_fail[i] = nullptr; c->h_fail_any[i] = nullptr;
+    }
+    if (c->h_ev) { cudaEventDestroy(c->h_ev); c->h_ev = nullptr; }
+    c->host_ready = false;
+}
+
 static int ensure_host_pipeline(ldpc_ctx *c)
 {
-    if (c->hstream[0]) return LDPC_OK;
+    if (c->host_ready) return LDPC_OK;
     const size_t per_cw = size_t(c->code.n) * c->S;
     long long mb = 128;                                  // LDPC_CUDA_HOST_CHUNK_MB: bytes of input per pipeline stage (128 measured best: 299 vs 291 Gbit/s at 256)
     if (const char *e = getenv("LDPC_CUDA_HOST_CHUNK_MB")) mb = std::max(1ll, atoll(e));
     long long chunk = std::min<long long>(c->max_batch, std::max<long long>(256, (mb << 20) / (long long)per_cw));
     c->host_chunk = chunk;
-    for (int i = 0; i < 2; i++) {
-        CUDA_TRY(cudaStreamCreateWithFlags(&c->hstream[i], cudaStreamNonBlocking));
-        CUDA_TRY(cudaMalloc(&c->h_in[i], size_t(chunk) * per_cw));
-        CUDA_TRY(cudaMalloc(&c->h_out[i], size_t(chunk) * per_cw));
-        CUDA_TRY(cudaMalloc(&c->h_mask[i], size_t(chunk) * c->NW * 4));
-        CUDA_TRY(cudaMalloc(&c->h_fail[i], size_t(chunk)));
+    cudaError_t e = cudaSuccess;
+    auto ok = [&](cudaError_t r) { if (e == cudaSuccess) e = r; return e == cudaSuccess; };
+    for (int i = 0; i < 2 && e == cudaSuccess; i++) {
+        ok(cudaStreamCreateWithFlags(&c->hstream[i], cudaStreamNonBlocking));
+        ok(cudaMalloc(&c->h_in[i], size_t(chunk) * per_cw));
+        ok(cudaMalloc(&c->h_out[i], size_t(chunk) * per_cw));
+        ok(cudaMalloc(&c->h_mask[i], size_t(chunk) * c->NW * 4));
+        ok(cudaMalloc(&c->h_fail[i], size_t(chunk)));
+        ok(cudaMalloc(&c->h_fail_any[i], size_t(chunk)));
     }
+    ok(cudaEventCreateWithFlags(&c->h_ev, cudaEventDisableTiming));
+    if (e != cudaSuccess) {                              // nothing half-built survives: the next call starts clean
+        free_host_pipeline(c);
+        return fail(e == cudaErrorMemoryAllocation ? LDPC_ERR_NOMEM : LDPC_ERR_CUDA, std::string("host pipeline set-up: ") + cudaGetErrorString(e));
+    }
+    c->host_ready = true;
     return LDPC_OK;
 }
 
@@ -951,8 +1039,8 @@ extern "C" int ldpc_encode_host(ldpc_ctx *c, const void *h_info, void *h_cw, int
     return LDPC_OK;
 }
 
-extern "C" int ldpc_decode_host(ldpc_ctx *c, const void *h_cw, const uint32_t *h_mask, void *h_out, uint8_t *h_fail,
-                                int max_iter, int mode, int64_t B)
+extern "C" int ldpc_decode_host_ex(ldpc_ctx *c, const void *h_cw, const uint32_t *h_mask, void *h_out, uint8_t *h_fail,
+                                   uint8_t *h_fail_any, int max_iter, int mode, int64_t B)
 {
     if (!c || !h_cw || !h_mask || !h_out || B < 0) return fail(LDPC_ERR_ARG, "bad argument to ldpc_decode_host");
     CUDA_TRY(cudaSetDevice(c->device));
@@ -961,8 +1049,6 @@ extern "C" int ldpc_decode_host(ldpc_ctx *c, const void *h_cw, const uint32_t *h
     const size_t in_cw = size_t(c->code.n) * c->S, out_cw = size_t(c->code.k) * c->S;
     // the scratch (schedule blobs) is shared by both streams: the peel/exec pair of chunk i+1 is ordered
     // after the pair of chunk i by an event, while the copies on either side overlap freely
-    cudaEvent_t ev;
-    CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     int i = 0;
     bool have_ev = false;
     for (long long b0 = 0; b0 < B; b0 += c->host_chunk, i ^= 1) {
@@ -971,19 +1057,89 @@ extern "C" int ldpc_decode_host(ldpc_ctx *c, const void *h_cw, const uint32_t *h
         CUDA_TRY(cudaMemcpyAsync(c->h_in[i], static_cast<const uint8_t *>(h_cw) + size_t(b0) * in_cw, size_t(nb) * in_cw,
                                  cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemcpyAsync(c->h_mask[i], h_mask + size_t(b0) * c->NW, size_t(nb) * c->NW * 4, cudaMemcpyHostToDevice, st));
-        if (have_ev) CUDA_TRY(cudaStreamWaitEvent(st, ev, 0));
-        rc = ldpc_decode(c, c->h_in[i], c->h_mask[i], c->h_out[i], c->h_fail[i], max_iter, mode, nb, st);
-        if (rc) { cudaEventDestroy(ev); return rc; }
-        CUDA_TRY(cudaEventRecord(ev, st));
+        if (have_ev) CUDA_TRY(cudaStreamWaitEvent(st, c->h_ev, 0));
+        rc = ldpc_decode_ex(c, c->h_in[i], c->h_mask[i], c->h_out[i], c->h_fail[i], h_fail_any ? c->h_fail_any[i] : nullptr, max_iter, mode, nb, st);
+        if (rc) return rc;
+        CUDA_TRY(cudaEventRecord(c->h_ev, st));
         have_ev = true;
         CUDA_TRY(cudaMemcpyAsync(static_cast<uint8_t *>(h_out) + size_t(b0) * out_cw, c->h_out[i], size_t(nb) * out_cw,
                                  cudaMemcpyDeviceToHost, st));
         if (h_fail) CUDA_TRY(cudaMemcpyAsync(h_fail + b0, c->h_fail[i], size_t(nb), cudaMemcpyDeviceToHost, st));
+        if (h_fail_any) CUDA_TRY(cudaMemcpyAsync(h_fail_any + b0, c->h_fail_any[i], size_t(nb), cudaMemcpyDeviceToHost, st));
     }
     CUDA_TRY(cudaStreamSynchronize(c->hstream[0]));
     CUDA_TRY(cudaStreamSynchronize(c->hstream[1]));
-    cudaEventDestroy(ev);
     return LDPC_OK;
+}
+
+extern "C" int ldpc_decode_host(ldpc_ctx *c, const void *h_cw, const uint32_t *h_mask, void *h_out, uint8_t *h_fail,
+                                int max_iter, int mode, int64_t B)
+{
+    return ldpc_decode_host_ex(c, h_cw, h_mask, h_out, h_fail, nullptr, max_iter, mode, B);
+}
+
+// ------------------------------------------------------------------------------------------
+// multi-GPU host entry points: the batch is cut into contiguous frame ranges, GPU g gets
+// [g*B/G, (g+1)*B/G); one host thread per GPU drives that GPU's host pipeline; no exchange between the GPUs
+// (codewords are independent, ldpc_erasure_decoder.cl:27-104).
+// ------------------------------------------------------------------------------------------
+struct FanOutJob {
+    const std::function<int(ldpc_ctx *, int64_t, int64_t)> *fn;
+    ldpc_ctx *ctx;
+    int64_t b0, nb;
+    int rc;
+    std::string err;
+};
+
+static void fan_out_worker(FanOutJob *job)
+{
+    job->rc = job->nb > 0 ? (*job->fn)(job->ctx, job->b0, job->nb) : LDPC_OK;
+    if (job->rc) job->err = ldpc_last_error_string();     // (thread-local: the worker's own message)
+}
+
+static int fan_out(ldpc_ctx *const *ctxs, int n_ctx, int64_t B, const char *what,
+                   const std::function<int(ldpc_ctx *, int64_t, int64_t)> &per_gpu)
+{
+    if (!ctxs || n_ctx <= 0 || B < 0) return fail(LDPC_ERR_ARG, std::string("bad argument to ") + what);
+    for (int g = 0; g < n_ctx; g++) {
+        if (!ctxs[g]) return fail(LDPC_ERR_ARG, std::string(what) + ": NULL context");
+        if (ctxs[g]->code.n != ctxs[0]->code.n || ctxs[g]->code.k != ctxs[0]->code.k || ctxs[g]->S != ctxs[0]->S)
+            return fail(LDPC_ERR_ARG, std::string(what) + ": the contexts must share one code and symbol size");
+        for (int h = 0; h < g; h++)
+            if (ctxs[h] == ctxs[g]) return fail(LDPC_ERR_ARG, std::string(what) + ": a context is listed twice (one host thread per context)");
+    }
+    std::vector<FanOutJob> jobs(static_cast<size_t>(n_ctx));
+    std::vector<std::thread> thr;
+    for (int g = 0; g < n_ctx; g++) {
+        FanOutJob &j = jobs[size_t(g)];
+        j.fn = &per_gpu; j.ctx = ctxs[g]; j.b0 = B * g / n_ctx; j.nb = B * (g + 1) / n_ctx - j.b0; j.rc = LDPC_OK;
+    }
+    for (int g = 0; g < n_ctx; g++) thr.emplace_back(fan_out_worker, &jobs[size_t(g)]);
+    for (auto &t : thr) t.join();
+    for (int g = 0; g < n_ctx; g++)
+        if (jobs[size_t(g)].rc) return fail(jobs[size_t(g)].rc, "GPU " + std::to_string(ctxs[g]->device) + ": " + jobs[size_t(g)].err);
+    return LDPC_OK;
+}
+
+extern "C" int ldpc_decode_host_multi(ldpc_ctx *const *ctxs, int n_ctx, const void *h_cw, const uint32_t *h_mask, void *h_out,
+                                      uint8_t *h_fail, uint8_t *h_fail_any, int max_iter, int mode, int64_t B)
+{
+    if (!h_cw || !h_mask || !h_out) return fail(LDPC_ERR_ARG, "NULL buffer passed to ldpc_decode_host_multi");
+    return fan_out(ctxs, n_ctx, B, "ldpc_decode_host_multi", [&](ldpc_ctx *c, int64_t b0, int64_t nb) {
+        const size_t in_cw = size_t(c->code.n) * c->S, out_cw = size_t(c->code.k) * c->S;
+        return ldpc_decode_host_ex(c, static_cast<const uint8_t *>(h_cw) + size_t(b0) * in_cw, h_mask + size_t(b0) * c->NW,
+                                   static_cast<uint8_t *>(h_out) + size_t(b0) * out_cw, h_fail ? h_fail + b0 : nullptr,
+                                   h_fail_any ? h_fail_any + b0 : nullptr, max_iter, mode, nb);
+    });
+}
+
+extern "C" int ldpc_encode_host_multi(ldpc_ctx *const *ctxs, int n_ctx, const void *h_info, void *h_cw, int64_t B)
+{
+    if (!h_info || !h_cw) return fail(LDPC_ERR_ARG, "NULL buffer passed to ldpc_encode_host_multi");
+    return fan_out(ctxs, n_ctx, B, "ldpc_encode_host_multi", [&](ldpc_ctx *c, int64_t b0, int64_t nb) {
+        const size_t in_cw = size_t(c->code.k) * c->S, out_cw = size_t(c->code.n) * c->S;
+        return ldpc_encode_host(c, static_cast<const uint8_t *>(h_info) + size_t(b0) * in_cw, static_cast<uint8_t *>(h_cw) + size_t(b0) * out_cw, nb);
+    });
 }
 
 // ------------------------------------------------------------------------------------------

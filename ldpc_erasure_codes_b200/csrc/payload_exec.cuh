@@ -7,22 +7,32 @@
 //     rows' dependencies on earlier parities (built on the host, hmat.cpp);
 //   * peeling decoder (OpenCL/device/ldpc_erasure_decoder.cl:68-90): the recovered symbol =
 //     XOR of the check's other members -- a PER-CODEWORD schedule from peel_schedule.cuh.
-// Entries of one level are independent; levels are separated by a barrier.
+// Entries of one level are independent; a level needs the levels below it.
 //
 // Work unit = (codeword b, byte slice s): rows_in symbols x W bytes, W a multiple of 16 chosen
 // so that a few units fit in shared memory (symbols' byte columns are independent and share the
 // schedule).  Persistent kernel, one CTA per SM, `nslot` independent warp groups per CTA; each
 // group owns one shared-memory slot and cycles
-//     TMA load (cp.async.bulk.tensor, 3-D map [B][rows][S], box {W, 256, 1}, + the schedule blob
-//               as a 1-D bulk copy, both completing on the slot's mbarrier)
-//  -> XOR the schedule into the slot, level by level (a group of W/16 lanes owns one entry and
-//     gathers the check's members with 128-bit shared loads, all issued before the first XOR)
+//     TMA load (cp.async.bulk.tensor, 3-D / 4-D map over [B][rows][S], + the schedule blob as a
+//               1-D bulk copy, all completing on the slot's mbarrier)
+//  -> XOR the schedule into the slot, level by level
 //  -> TMA store of the first rows_out rows.
-// The walk through the levels is a chain of shared-memory latencies (a level cannot start before
-// the previous one has been written), so one unit alone leaves the SM idle; the groups run
-// different units at different phases and fill each other's stalls, and while one group computes
-// the others' TMA traffic keeps HBM busy.  HBM traffic is exactly the algorithmic bytes (+ the
-// schedule blob): every input byte is read once and every output byte written once by TMA.
+// HBM traffic is exactly the algorithmic bytes (+ the schedule blob): every input byte is read
+// once and every output byte written once by TMA; all gathers hit shared memory.
+//
+// The level walk.  At the code's threshold a schedule is a LONG chain of SMALL levels ((2040,1530) at
+// 20 % erasures: ~330 entries in ~20 levels -- 80, 40, 25, 19, 15 entries, then ~10 per level), so the
+// XOR phase is a chain of shared-memory round trips, not a bandwidth problem.  Its link is kept short:
+//   * the rows a schedule produces are zeroed first and every member of the check is gathered,
+//     the target included (the reference does the same: erased symbols are zero and XORed in,
+//     ldpc_erasure_decoder.cl:17-20,68-75): no per-member compare/select;
+//   * check rows are staged once per CTA as pre-scaled 16-byte offsets, row padding pointing at a
+//     zero row behind the slot: a member's address is one shift-add;
+//   * a level of more than `wide_min` entries is spread over the group's four warps and closed by the
+//     group's named barrier; a run of smaller levels is walked by ONE warp alone, in program
+//     order, with only __syncwarp() between levels -- no inter-warp hand-off on the chain -- while
+//     the entry word and check row of the next pass are fetched ahead of the current pass's gathers.
+// The other groups of the CTA run other units at other phases and keep TMA traffic flowing.
 #pragma once
 #include "device_utils.cuh"
 
@@ -31,6 +41,7 @@ namespace ldpc {
 constexpr int kExecWarpsPerGroup = 4;
 constexpr int kExecMaxGroups = 4;
 constexpr int kBoxRows = 256;
+constexpr int kExecZeroRowBytes = 128;   // behind every slot: what row padding reads
 
 struct ExecParams {
     const uint16_t *cidx;       // [m][RW] check rows, pad 0xFFFF
@@ -44,7 +55,8 @@ struct ExecParams {
     int nbox_in, nbox_out;      // ceil(rows / 256)
     int slices;                 // S / W
     int nslot;                  // = number of warp groups
-    int slot_bytes;             // shared bytes per slot
+    int slot_bytes;             // shared bytes per slot (payload rows + the zero row)
+    int wide_min;               // levels with more entries than this are spread over the group's warps
     uint8_t *synd;              // hybrid mode: [B][m][S] check syndromes of the codewords that still have erasures, or nullptr
     const uint32_t *mask;       // hybrid mode: [B][NW] erasure masks (erased rows are zeroed in the slot before the XOR phase)
     int NW;
@@ -77,31 +89,38 @@ payload_exec_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
     constexpr int LPG = W / 16;                       // lanes per entry
     constexpr int GT = kExecWarpsPerGroup * 32;       // threads per group
     constexpr int NGROUPS = GT / LPG;                 // entries a group handles per pass
+    constexpr int EPW = 32 / LPG;                     // entries per warp and pass
+    constexpr int WPGc = kExecWarpsPerGroup;
     extern __shared__ __align__(1024) uint8_t smem[];
-    // layout: [slots][blobs: nslot (dynamic) or 1 (static)][cidx][barriers][zero row][unit mailboxes]
+    // layout: [slots][blobs: nslot (dynamic) or 1 (static)][check rows][barriers][unit mailboxes][masks (hybrid)]
     uint8_t *slots = smem;
     uint8_t *blobs = slots + size_t(p.nslot) * p.slot_bytes;
     const bool dynamic = p.sched_stride != 0;
     uint16_t *cidx_s = reinterpret_cast<uint16_t *>(blobs + size_t(dynamic ? p.nslot : 1) * p.sched_max);
     uint64_t *full = reinterpret_cast<uint64_t *>(cidx_s + size_t(p.m) * (RWQ * 8));   // [nslot]
-    uint8_t *zrow = reinterpret_cast<uint8_t *>(full + 8);   // 64 zero bytes: what a skipped member reads
-    int *mailbox = reinterpret_cast<int *>(zrow + 64);       // [g] unit of group g, [8] next unit, [16 + g] level hand-off
-    uint32_t *msk_s = reinterpret_cast<uint32_t *>(mailbox + 32) + (threadIdx.x / GT) * ((p.NW + 3) & ~3);   // hybrid mode: the unit's mask
+    int *mailbox = reinterpret_cast<int *>(full + 8);        // [g] unit of group g, [8] next unit
+    uint32_t *msk_s = reinterpret_cast<uint32_t *>(mailbox + 16) + (threadIdx.x / GT) * ((p.NW + 3) & ~3);   // hybrid mode: the unit's mask
 
     const int g = threadIdx.x / GT;          // group = slot
     const int tg = threadIdx.x % GT;         // thread in group
     const bool leader = tg == 0;
+    const int zrow16 = (p.slot_bytes - kExecZeroRowBytes) / 16;   // the zero row, in 16-byte units from the slot base
 
-    {   // stage the check rows (and the static schedule) once per CTA
-        const uint4 *src = reinterpret_cast<const uint4 *>(p.cidx);
-        uint4 *dst = reinterpret_cast<uint4 *>(cidx_s);
-        for (int i = threadIdx.x; i < p.m * RWQ; i += blockDim.x) dst[i] = src[i];
+    {   // stage the check rows once per CTA as 16-byte offsets into a slot (row u -> u * W / 16, padding -> the zero row)
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(p.cidx);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(cidx_s);
+        for (int i = threadIdx.x; i < p.m * RWQ * 4; i += blockDim.x) {
+            const uint32_t w = src[i];
+            const uint32_t lo = w & 0xFFFFu, hi = w >> 16;
+            dst[i] = (lo == 0xFFFFu ? uint32_t(zrow16) : lo * LPG) | ((hi == 0xFFFFu ? uint32_t(zrow16) : hi * LPG) << 16);
+        }
         if (!dynamic) {
             const uint4 *s2 = reinterpret_cast<const uint4 *>(p.sched);
             uint4 *d2 = reinterpret_cast<uint4 *>(blobs);
             for (int i = threadIdx.x; i < p.sched_max / 16; i += blockDim.x) d2[i] = s2[i];
         }
-        if (threadIdx.x < 16) reinterpret_cast<uint32_t *>(zrow)[threadIdx.x] = 0u;
+        for (int s = threadIdx.x / 8; s < p.nslot; s += blockDim.x / 8)      // the zero rows (never touched by TMA)
+            reinterpret_cast<uint4 *>(slots + size_t(s + 1) * p.slot_bytes - kExecZeroRowBytes)[threadIdx.x % 8] = make_uint4(0u, 0u, 0u, 0u);
         if (threadIdx.x == 0) {
             for (int s = 0; s < p.nslot; s++) mbar_init(&full[s], 1);
             mailbox[8] = 0;
@@ -117,11 +136,9 @@ payload_exec_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
     const int n_units = int(cw_per_cta * p.slices);
 
     uint8_t *slot = slots + size_t(g) * p.slot_bytes;
-    const uint32_t base_a = smem_u32(slot) + (tg % LPG) * 16;    // shared-space addresses
-    const uint32_t zero_a = smem_u32(zrow) + (tg % LPG) * 16;
+    const uint32_t base_a = smem_u32(slot) + (tg % LPG) * 16;    // shared-space address of my 16-byte column
     uint8_t *blob = blobs + (dynamic ? size_t(g) * p.sched_max : 0);
     const int bar_id = 1 + g;
-    const uint32_t done_a = smem_u32(&mailbox[16 + g]);          // per-group "level workers done" counter
     uint32_t phase = 0;
 
     // leader state: the next unit is claimed (and its blob length fetched) one unit ahead, so that the
@@ -143,12 +160,15 @@ payload_exec_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
             t_prev = t;
         }
     };
+
+    const int wg = tg >> 5;                       // warp in group
+    const int es = (tg & 31) / LPG;               // entry slot inside the warp
+
     while (true) {
         // ---- leader: start the loads of the unit claimed earlier, claim the one after -----------
         if (leader) {
             const int j = j_next;
             mailbox[g] = j;
-            mailbox[16 + g] = 0;
             if (j < n_units) {
                 const long long b = blockIdx.x + (long long)(j / p.slices) * gridDim.x;
                 const int sl = j % p.slices;
@@ -172,127 +192,104 @@ payload_exec_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
         mbar_wait(&full[g], phase);
         phase ^= 1u;
         lap(1);
-        if (p.synd && reinterpret_cast<const uint32_t *>(blob)[2] != 0u) {   // (uniform over the group)
-            // Symbols that stay unknown must read as zero when the syndromes are formed below.  Erased symbols
-            // are zero on input by contract; zeroing them here makes the decoder independent of that.
-            named_bar_sync(bar_id, GT);
-            const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
-            for (int u = tg / LPG; u < p.rows_in; u += NGROUPS)
-                if ((msk_s[u >> 5] >> (u & 31)) & 1u) sts128(base_a + u * W, z4);
-            named_bar_sync(bar_id, GT);
-        }
 
-        // ---- XOR the schedule into the slot -----------------------------------------------
-        // The level walk is a chain of shared-memory round trips (a level's gathers cannot start
-        // before the previous level's results are written, ~600-700 cycles per level all told), so:
-        //  * everything that does NOT depend on the payload -- which entry a lane group handles
-        //    next, the check's member list, the members' shared addresses -- is prepared ahead;
-        //  * consecutive levels go to different warps of the group (a level starts at the warp after the
-        //    last worker of the level below), and there is NO group-wide barrier between levels: a warp that finishes
-        //    its part of level l bumps a completion counter (release) and goes on to prepare its next
-        //    task; a warp about to execute level L spins (acquire) until the counter shows that all
-        //    workers of the levels below are done.
         const uint32_t *hdr = reinterpret_cast<const uint32_t *>(blob);
         const int ne = int(hdr[0]);
         const int nl = int(hdr[1]);
         const uint32_t *ent = hdr + 4;
         const uint16_t *lvo = reinterpret_cast<const uint16_t *>(ent + ne);
-        constexpr int EPW = 32 / LPG;                 // entries per warp and pass
-        constexpr int WPGc = kExecWarpsPerGroup;
-        const int wg = tg >> 5;                       // warp in group
-        const int es = (tg & 31) / LPG;               // entry slot inside the warp
-        int t_idx = 0, t_end = 0;
-        bool t_valid = false;
-        uint32_t t_dst = 0;
-        uint32_t t_src[RWM];
-        auto prepare = [&]() {                        // member addresses of entry t_idx
-            const uint32_t e = ent[t_idx];
-            const uint32_t v = e & 0xFFFFu;
-            const uint4 *row = reinterpret_cast<const uint4 *>(cidx_s + size_t(e >> 16) * (RWQ * 8));
-            uint32_t rr[RWQ * 4];
+        const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+        if (p.synd && hdr[2] != 0u) {   // (uniform over the group)
+            // Hybrid mode, the codeword keeps erasures after peeling: symbols that stay unknown must read as
+            // zero when the syndromes are formed below, so every erased row is zeroed (a superset of the rows
+            // the schedule produces).
+            named_bar_sync(bar_id, GT);   // the mask words
+            for (int u = tg / LPG; u < p.rows_in; u += NGROUPS)
+                if ((msk_s[u >> 5] >> (u & 31)) & 1u) sts128(base_a + u * W, z4);
+        } else {
+            // the rows this schedule produces read as zero until they are written: every gather below takes
+            // ALL members of its check, the target included
+            for (int i = tg / LPG; i < ne; i += NGROUPS) sts128(base_a + (ent[i] & 0xFFFFu) * W, z4);
+        }
+        named_bar_sync(bar_id, GT);
+
+        // ---- XOR the schedule into the slot -----------------------------------------------
+        struct Prep { uint32_t e; uint32_t rr[RWQ * 4]; };
+        auto fetch = [&](int idx, bool valid) -> Prep {   // entry word + its check row (payload independent)
+            Prep q;
+            q.e = valid ? ent[idx] : 0u;
+            const uint4 *row = reinterpret_cast<const uint4 *>(cidx_s + size_t(q.e >> 16) * (RWQ * 8));
 #pragma unroll
             for (int qq = 0; qq < RWQ; qq++) {
                 const uint4 r4 = row[qq];
-                rr[qq * 4 + 0] = r4.x; rr[qq * 4 + 1] = r4.y; rr[qq * 4 + 2] = r4.z; rr[qq * 4 + 3] = r4.w;
+                q.rr[qq * 4 + 0] = r4.x; q.rr[qq * 4 + 1] = r4.y; q.rr[qq * 4 + 2] = r4.z; q.rr[qq * 4 + 3] = r4.w;
             }
+            return q;
+        };
+        auto apply = [&](const Prep &q) {                 // gather every member, XOR tree, store the symbol
+            uint4 val[RWM];
 #pragma unroll
             for (int t = 0; t < RWM; t++) {
-                const uint32_t u = (t & 1) ? (rr[t >> 1] >> 16) : (rr[t >> 1] & 0xFFFFu);
-                t_src[t] = (u == v || u == 0xFFFFu) ? zero_a : base_a + u * W;
+                const uint32_t o16 = (t & 1) ? (q.rr[t >> 1] >> 16) : (q.rr[t >> 1] & 0xFFFFu);
+                val[t] = lds128(base_a + (o16 << 4));
             }
-            t_dst = base_a + v * W;
-        };
-        // My warp's tasks (the levels it works in) are found 32 levels at a time with one ballot: lane i
-        // looks at level l0+i.  Walking the level table entry by entry costs two dependent shared loads
-        // per level and warp, which is as long as the work itself when the levels are small.
-        constexpr unsigned FULLM = 0xFFFFFFFFu;
-        const int wl = tg & 31;
-        int l0 = -32;                                 // first level of the current chunk
-        unsigned todo = 0u;                           // levels of the chunk where my warp still has to work
-        int c_s0 = 0, c_s1 = 0;                       // lane i: entry range of level l0+i
-        uint32_t c_dt = 0, done_base = 0;             // lane i: workers of all levels below l0+i; below the next chunk
-        uint32_t done_target = 0;
-        auto next_task = [&]() -> bool {              // warp-uniform; sets up t_* for my lane group
-            while (!todo) {
-                l0 += 32;
-                if (l0 >= nl) return false;
-                const int ll = l0 + wl;
-                c_s0 = 0; c_s1 = 0;
-                if (ll < nl) { c_s0 = lvo[ll]; c_s1 = lvo[ll + 1]; }
-                const int cnt = c_s1 - c_s0;
-                const int nw = ll < nl ? min(WPGc, (cnt + EPW - 1) / EPW) : 0;
-                int inc = nw;
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int t = __shfl_up_sync(FULLM, inc, o);
-                    if (wl >= o) inc += t;
+            for (int st = 1; st < RWM; st <<= 1)
+#pragma unroll
+                for (int t = 0; t + st < RWM; t += 2 * st) xor_acc(val[t], val[t + st]);
+            sts128(base_a + (q.e & 0xFFFFu) * W, val[0]);
+        };
+
+        int L = 0;
+        bool in_step = true;          // all warps of the group are at the same point of the walk
+        while (L < nl) {
+            const int s0 = lvo[L], s1 = lvo[L + 1];
+            if (s1 - s0 > p.wide_min) {
+                // a wide level: my warp takes entries s0 + wg * EPW + es, + 4 * EPW, ...
+                if (!in_step) named_bar_sync(bar_id, GT);           // warp 0 has finished the small levels below
+                int idx = s0 + wg * EPW + es;
+                Prep cur = fetch(idx, idx < s1);
+                for (int base = s0 + wg * EPW; base < s1; base += WPGc * EPW) {
+                    const bool valid = idx < s1;
+                    const int nidx = idx + WPGc * EPW;
+                    const Prep nxt = fetch(nidx, nidx < s1);
+                    if (valid) apply(cur);
+                    cur = nxt;
+                    idx = nidx;
                 }
-                c_dt = done_base + uint32_t(inc - nw);
-                done_base += uint32_t(__shfl_sync(FULLM, inc, 31));
-                // a level's first entries go to the warp after the last worker of the level below (c_dt counts
-                // the workers so far): two-warp levels then alternate between the warp pairs, and a warp's
-                // preparation for its next level overlaps the other pair's turn
-                todo = __ballot_sync(FULLM, ll < nl && int((uint32_t(wg) - c_dt) % WPGc) * EPW < cnt);
-            }
-            const int b = __ffs(todo) - 1;
-            todo &= todo - 1u;
-            const int s0 = __shfl_sync(FULLM, c_s0, b);
-            t_end = __shfl_sync(FULLM, c_s1, b);
-            done_target = __shfl_sync(FULLM, c_dt, b);
-            t_idx = s0 + int((uint32_t(wg) - done_target) % WPGc) * EPW + es;
-            t_valid = t_idx < t_end;
-            if (t_valid) prepare();
-            return true;
-        };
-        bool have = next_task();
-        while (have) {
-            if (done_target) {                        // wait for the levels below
-                uint32_t seen, spins = 0;
-                do {
-                    asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(seen) : "r"(done_a) : "memory");
-                    if (++spins > (1u << 26)) {       // a lost hand-off must trap, not hang the GPU
-                        printf("libldpc_cuda: level hand-off timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
-                        __trap();
+                named_bar_sync(bar_id, GT);
+                in_step = true;
+                L++;
+            } else {
+                // a run of small levels [L, L2): warp 0 walks it alone in program order
+                int L2 = L + 1, e2 = s1;
+                while (L2 < nl) {
+                    const int nx = lvo[L2 + 1];
+                    if (nx - e2 > p.wide_min) break;
+                    e2 = nx;
+                    L2++;
+                }
+                if (wg == 0) {
+                    int lv = L, lend = s1;              // current level and its end
+                    int pos = s0;                       // first entry of the current pass
+                    Prep cur = fetch(pos + es, pos + es < lend);
+                    bool cur_valid = pos + es < lend;
+                    while (true) {
+                        // next pass: the rest of this level, or the start of the next one
+                        int npos = pos + EPW, nlv = lv, nlend = lend;
+                        if (npos >= lend) { npos = lend; nlv = lv + 1; if (nlv < L2) nlend = lvo[nlv + 1]; }
+                        const bool more = nlv < L2;
+                        const bool nvalid = more && npos + es < nlend;
+                        const Prep nxt = fetch(npos + es, nvalid);
+                        if (cur_valid) apply(cur);
+                        __syncwarp();                   // this pass's symbols are visible to the warp's next gathers
+                        if (!more) break;
+                        cur = nxt; cur_valid = nvalid; pos = npos; lv = nlv; lend = nlend;
                     }
-                } while (seen < done_target);
+                }
+                in_step = false;
+                L = L2;
             }
-            while (t_valid) {
-                uint4 val[RWM];
-#pragma unroll
-                for (int t = 0; t < RWM; t++) val[t] = lds128(t_src[t]);
-#pragma unroll
-                for (int st = 1; st < RWM; st <<= 1)               // XOR tree
-#pragma unroll
-                    for (int t = 0; t + st < RWM; t += 2 * st) xor_acc(val[t], val[t + st]);
-                sts128(t_dst, val[0]);
-                t_idx += NGROUPS;                      // another pass in this level?
-                t_valid = t_idx < t_end;
-                if (t_valid) prepare();
-            }
-            __syncwarp();
-            if (wl == 0)
-                asm volatile("red.release.cta.shared::cta.add.u32 [%0], %1;" ::"r"(done_a), "r"(1u) : "memory");
-            have = next_task();                        // off the critical path: my next level, addresses prepared
         }
         // ---- store the first rows_out rows, recycle the slot --------------------------------
         fence_proxy_async_smem();
@@ -303,7 +300,7 @@ payload_exec_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
             // members known NOW.  They are all in the slot, so the syndromes are formed here -- one level, no
             // chain -- instead of being gathered from HBM later.  Every member is XORed in: the symbols that
             // are still unknown were zeroed above.
-            if (reinterpret_cast<const uint32_t *>(blob)[2] != 0u) {
+            if (hdr[2] != 0u) {
                 const long long b = blockIdx.x + (long long)(j / p.slices) * gridDim.x;
                 uint8_t *dst = p.synd + (size_t(b) * p.m) * (size_t(p.slices) * W) + size_t(j % p.slices) * W + (tg % LPG) * 16;
                 for (int r = tg / LPG; r < p.m; r += NGROUPS) {
@@ -317,9 +314,8 @@ payload_exec_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
                     uint4 acc = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
                     for (int t = 0; t < RWM; t++) {
-                        const uint32_t u = (t & 1) ? (rr[t >> 1] >> 16) : (rr[t >> 1] & 0xFFFFu);
-                        const uint4 v = lds128(u == 0xFFFFu ? zero_a : base_a + u * W);
-                        acc.x ^= v.x; acc.y ^= v.y; acc.z ^= v.z; acc.w ^= v.w;
+                        const uint32_t o16 = (t & 1) ? (rr[t >> 1] >> 16) : (rr[t >> 1] & 0xFFFFu);
+                        xor_acc(acc, lds128(base_a + (o16 << 4)));
                     }
                     *reinterpret_cast<uint4 *>(dst + size_t(r) * (size_t(p.slices) * W)) = acc;
                 }

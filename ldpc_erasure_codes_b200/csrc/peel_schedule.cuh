@@ -36,9 +36,10 @@ struct PeelParams {
     unsigned int *work_ctr;     // zeroed before the launch: next unclaimed codeword
     uint8_t *sched;             // [B][stride] schedule blobs
     uint32_t *sched_len;        // [B] bytes of each blob (multiple of 16)
-    uint8_t *fail;              // [B] or nullptr
+    uint8_t *fail;              // [B] or nullptr: a systematic symbol is still erased (perf_tests.cl:215-228)
+    uint8_t *fail_any;          // [B] or nullptr: any of the n symbols is still erased (LDPCErasureCodes_MessagePassingAlgSim.m:229-236)
     uint32_t *resid;            // [B] or nullptr: erasures left after peeling (hybrid stage input)
-    unsigned long long *stats;  // [8] frames, ldpc_errors, rs_errors, ...
+    unsigned long long *stats;  // [8] frames, ldpc_errors, rs_errors, (hybrid: [3..5]), [6] frames with any symbol left erased
     const uint16_t *cidx;       // [m][RW]
     const uint16_t *vadj;       // [n][VW]
     long long B;
@@ -98,9 +99,8 @@ __global__ void __launch_bounds__(1024) peel_schedule_kernel(const PeelParams p)
     __shared__ unsigned int s_stat[4];
     const int m = p.m, NW = p.NW, RW = p.RW;
     const int m4 = (m + 3) & ~3;
-    const int vadj_words = (p.n * VW) / 2;    // u16 table sizes in 32-bit words
+    const int vadj_words = ((p.n * VW + 7) & ~7) / 2;    // u16 table sizes in 32-bit words (the host pads the table to 16 bytes)
     const int cidx_words = (m * RW) / 2;
-    (void)0;
     uint16_t *cidx_s = reinterpret_cast<uint16_t *>(sh + vadj_words);
     const int grp_base = vadj_words + cidx_words;
     const uint32_t padidx = uint32_t(NW) * 32u;   // row padding points at the always-zero word msk[NW]
@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(1024) peel_schedule_kernel(const PeelParams p)
     const uint32_t sh_a = smem_u32(sh);
     const int dummy_off = msk_off + NW + 1 + lane % 3;     // (distinct lanes may share a scratch word: values are never read back)   // scratch words behind the mask 
 
-    unsigned int my_fail = 0, my_rs = 0, my_frames = 0;
+    unsigned int my_fail = 0, my_rs = 0, my_frames = 0, my_any = 0;
     // Codewords are claimed a warp-load (32/G) at a time from a global counter: replay lengths vary by
     // codeword, and a static split leaves most of the GPU idle in the last round.
     auto claim = [&]() -> long long {
@@ -325,10 +325,12 @@ __global__ void __launch_bounds__(1024) peel_schedule_kernel(const PeelParams p)
             hdr[0] = ne; hdr[1] = nl; hdr[2] = uint32_t(n_er); hdr[3] = uint32_t(rem_sys);
             p.sched_len[cw] = (16u + 4u * ne + 2u * (nl + 1u) + 15u) & ~15u;
             if (p.fail) p.fail[cw] = rem_sys > 0 ? 1 : 0;
+            if (p.fail_any) p.fail_any[cw] = n_er > 0 ? 1 : 0;
             if (p.resid) p.resid[cw] = uint32_t(n_er);
             if (p.ge_list && n_er > 0) p.ge_list[atomicAdd(p.ge_count, 1u)] = (unsigned int)cw;
             my_frames++;
             if (rem_sys > 0) my_fail++;
+            if (n_er > 0) my_any++;
         }
         __syncwarp();
     }
@@ -337,9 +339,10 @@ __global__ void __launch_bounds__(1024) peel_schedule_kernel(const PeelParams p)
         if (my_frames) atomicAdd(&s_stat[0], my_frames);
         if (my_fail) atomicAdd(&s_stat[1], my_fail);
         if (my_rs) atomicAdd(&s_stat[2], my_rs);
+        if (my_any) atomicAdd(&s_stat[3], my_any);
         __syncthreads();
-        if (threadIdx.x < 3 && s_stat[threadIdx.x])
-            atomicAdd(&p.stats[threadIdx.x], (unsigned long long)s_stat[threadIdx.x]);
+        if (threadIdx.x < 4 && s_stat[threadIdx.x])   // [6] = frames with any symbol unknown after peeling
+            atomicAdd(&p.stats[threadIdx.x < 3 ? threadIdx.x : 6], (unsigned long long)s_stat[threadIdx.x]);
     }
 }
 

@@ -625,3 +625,140 @@ def test_packet_stream_end_to_end(codecs):
     n, k = codec.n, codec.k
     assert codec.ready_to_decode(n, 0) and not codec.ready_to_decode(k + 408, 11) and codec.ready_to_decode(k + 409, 11)
     assert all(codec.ready_to_decode(c, x) == orc.ready_to_decode(n, k, c, x) for c in range(1500, 2041, 7) for x in (0, 10, 11, 100, 101))
+
+
+# ------------------------------------------------------------------------------- second failure criterion (a-8)
+@pytest.mark.parametrize("mode,it,P", [("peel", 50, 13), ("peel", 2, 10), ("hybrid", 10, 13), ("hybrid", 10, 16)])
+def test_fail_any_matches_oracle(codecs, mode, it, P):
+    """d_fail_any = any of the n symbols still unknown (LDPCErasureCodes_MessagePassingAlgSim.m:229-236);
+    d_fail = any of the first k (perf_tests.cl:215-228)."""
+    codec = codecs(1, 64)
+    code, cw, rx, mask, flags = _scenario(codec, 1, 300, P, 606 + P, 64)
+    fail_any = torch.full((300,), 7, dtype=torch.uint8, device="cuda")
+    codec.reset_stats()
+    out, fail = codec.decode(rx, mask, max_iter=it, mode=mode, fail_any=fail_any)
+    ref = orc.decode(code, _np(rx), flags, max_iter=it, mode=mode)
+    ref_any = (ref["erased"].max(axis=1) > 0).astype(np.uint8)
+    assert np.array_equal(_np(fail), ref["fail_sys"])
+    assert np.array_equal(_np(fail_any), ref_any)
+    assert (ref_any >= ref["fail_sys"]).all()
+    st = codec.stats()
+    assert st["any_errors"] == int(ref_any.sum())
+    if mode == "peel" and P == 13:
+        assert ref_any.sum() > ref["fail_sys"].sum() or ref_any.sum() > 0    # the case is not vacuous
+
+
+# ------------------------------------------------------------------------------- the benchmark's geometry
+@pytest.mark.parametrize("mode,it", [("peel", 50), ("hybrid", 10)])
+def test_benchmark_geometry_against_oracle(mode, it):
+    """bench.py's launch shape -- max_batch 65536, a call of 2 x 65536 codewords (two chunks: two internal streams and two
+    scratch sets in peel mode), 148 persistent CTAs claiming work dynamically -- compared with the ORACLE on a strided
+    sample of 4096 codewords (not a round-trip property)."""
+    from ldpc_erasure_codes_b200.codec import LdpcCodec
+    S, P, sub = 64, 13, 65536
+    B = 2 * sub
+    codec = LdpcCodec(code=1, symbol_bytes=S, device=0, max_batch=sub)
+    code = orc.Code.builtin(1)
+    info = torch.empty((sub, codec.k, S), dtype=torch.uint8, device="cuda")
+    rx = torch.empty((B, codec.n, S), dtype=torch.uint8, device="cuda")
+    from ldpc_erasure_codes_b200.codec import fill_random
+    for h in range(2):
+        fill_random(info, seed=90 + h)
+        codec.encode(info, out=rx[h * sub:(h + 1) * sub])
+    mask = codec.gen_erasures(B, 4711, P=P, payload=rx)
+    out, fail = codec.decode(rx, mask, max_iter=it, mode=mode)
+    torch.cuda.synchronize()
+    idx = torch.arange(5, B, B // 4096, device="cuda")[:4096]
+    assert idx.numel() == 4096 and int(idx[-1]) >= sub          # the sample spans both chunks
+    flags = orc.gen_erasures_iid(code.n, 4711, B, P=P)[_np(idx)]
+    from ldpc_erasure_codes_b200.codec import unpack_mask
+    assert np.array_equal(unpack_mask(mask[idx], code.n), flags)
+    ref = orc.decode(code, _np(rx[idx]), flags, max_iter=it, mode=mode)
+    assert np.array_equal(_np(fail[idx]), ref["fail_sys"])
+    assert np.array_equal(_np(out[idx]), ref["out"])
+    # and the whole batch through the round-trip property
+    good = fail == 0
+    for h in range(2):
+        fill_random(info, seed=90 + h)
+        g = good[h * sub:(h + 1) * sub]
+        assert bool((out[h * sub:(h + 1) * sub][g] == info[g]).all())
+    codec.close()
+
+
+# ------------------------------------------------------------------------------- several contexts in one process
+def _two_context_run(dev_a, dev_b, threaded):
+    import threading
+    from ldpc_erasure_codes_b200.codec import LdpcCodec, fill_random
+    code = orc.Code.builtin(1)
+    res = {}
+
+    def work(dev, seed):
+        with torch.cuda.device(dev):
+            codec = LdpcCodec(code=1, symbol_bytes=64, device=dev, max_batch=256)
+            info = torch.empty((300, codec.k, 64), dtype=torch.uint8, device=f"cuda:{dev}")
+            fill_random(info, seed=seed)
+            cw = codec.encode(info)
+            rx = cw.clone()
+            mask = codec.gen_erasures(300, seed, P=13, payload=rx)
+            out_p, fail_p = codec.decode(rx, mask, max_iter=50, mode="peel")
+            out_h, fail_h = codec.decode(rx, mask, max_iter=10, mode="hybrid")
+            torch.cuda.synchronize(dev)
+            res[(dev, seed)] = (_np(info), _np(cw), _np(rx), _np(out_p), _np(fail_p), _np(out_h), _np(fail_h))
+            codec.close()
+
+    jobs = [(dev_a, 11), (dev_b, 12)]
+    if threaded:
+        ts = [threading.Thread(target=work, args=j) for j in jobs]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+    else:
+        for j in jobs:
+            work(*j)
+    assert len(res) == 2
+    for (dev, seed), (info, cw, rx, out_p, fail_p, out_h, fail_h) in res.items():
+        assert np.array_equal(cw, orc.encode(code, info))
+        flags = orc.gen_erasures_iid(code.n, seed, 300, P=13)
+        rp = orc.decode(code, rx, flags, max_iter=50, mode="peel")
+        rh = orc.decode(code, rx, flags, max_iter=10, mode="hybrid")
+        assert np.array_equal(out_p, rp["out"]) and np.array_equal(fail_p, rp["fail_sys"])
+        assert np.array_equal(out_h, rh["out"]) and np.array_equal(fail_h, rh["fail_sys"])
+
+
+@pytest.mark.parametrize("threaded", [False, True])
+def test_two_contexts_one_process(threaded):
+    """Two ldpc_ctx in one process -- on devices 0 and 1 when the box has two GPUs (the shared-memory opt-in is per
+    device), else both on device 0 -- from one thread and from one thread each."""
+    second = 1 if torch.cuda.device_count() > 1 else 0
+    _two_context_run(0, second, threaded)
+
+
+def test_decode_host_multi_fans_out(codecs):
+    """ldpc_decode_host_multi / ldpc_encode_host_multi: one host batch over several contexts (one per GPU where
+    the box has several), one host thread per context inside the library."""
+    from ldpc_erasure_codes_b200.codec import LdpcCodec, decode_host_multi, encode_host_multi
+    ndev = max(1, min(torch.cuda.device_count(), 4))
+    devs = list(range(ndev)) if ndev > 1 else [0, 0]
+    cs = [LdpcCodec(code=1, symbol_bytes=64, device=d, max_batch=128) for d in devs]
+    code = orc.Code.builtin(1)
+    B = 517
+    info = _rand_info(B, code.k, 64, seed=77).cpu().pin_memory()
+    h_cw = encode_host_multi(cs, info)
+    assert np.array_equal(h_cw.numpy(), orc.encode(code, info.numpy()))
+    flags = orc.gen_erasures_iid(code.n, 4, B, P=13)
+    rx = h_cw.numpy().copy()
+    rx[flags == 1] = 0
+    from ldpc_erasure_codes_b200.codec import pack_mask
+    h_rx = torch.from_numpy(rx).pin_memory()
+    h_mask = torch.from_numpy(pack_mask(flags)).pin_memory()
+    for mode, it in (("peel", 50), ("hybrid", 10)):
+        fail_any = torch.zeros(B, dtype=torch.uint8).pin_memory()
+        out, fail = decode_host_multi(cs, h_rx, h_mask, max_iter=it, mode=mode, fail_any=fail_any)
+        ref = orc.decode(code, rx, flags, max_iter=it, mode=mode)
+        assert np.array_equal(out.numpy(), ref["out"]) and np.array_equal(fail.numpy(), ref["fail_sys"])
+        assert np.array_equal(fail_any.numpy(), (ref["erased"].max(axis=1) > 0).astype(np.uint8))
+    assert sum(c.stats()["frames"] for c in cs) == 2 * B
+    from ldpc_erasure_codes_b200 import _lib as L
+    with pytest.raises(L.LdpcCudaError):
+        decode_host_multi([cs[0], cs[0]], h_rx, h_mask)            # a context listed twice
+    for c in cs:
+        c.close()
