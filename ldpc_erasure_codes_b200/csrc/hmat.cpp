@@ -253,8 +253,8 @@ int build_code(int rows, int cols, const std::vector<int32_t> &col_ptr,
         code.max_row_weight = std::max(code.max_row_weight, w);
         if (w == 0 || code.col_idx[code.row_ptr[r + 1] - 1] != code.k + r) code.triangular = false;
     }
-    if (code.n > 65534 || code.m > 2047 || code.max_row_weight > 30) {   // (the peel kernel's 5-bit erased-member count keeps 31 as its "fired" mark)
-        err = "code outside kernel limits (n <= 65534, m <= 2047, row weight <= 30)";
+    if (code.n > kSchedMaxRow - 1 || code.m > 2047 || code.max_row_weight > 30) {   // (12-bit symbol indices in the peel state and the schedule records; the peel kernel's 5-bit erased-member count keeps 31 as its "fired" mark)
+        err = "code outside kernel limits (n <= 4094, m <= 2047, row weight <= 30)";
         return LDPC_ERR_UNSUPPORTED;
     }
     code.RW = (code.max_row_weight + 7) & ~7;
@@ -289,13 +289,53 @@ int build_code(int rows, int cols, const std::vector<int32_t> &col_ptr,
         std::vector<uint32_t> entries(rows);
         std::vector<uint16_t> pos(lvl_off.begin(), lvl_off.end());
         for (int r = 0; r < rows; r++) entries[pos[level[r] - 1]++] = uint32_t(code.k + r) | (uint32_t(r) << 16);
-        code.enc_blob.assign(size_t(sched_blob_max_bytes(rows)), 0);
-        uint32_t hdr[4] = {uint32_t(rows), uint32_t(nl), 0u, 0u};
-        memcpy(code.enc_blob.data(), hdr, 16);
-        memcpy(code.enc_blob.data() + 16, entries.data(), size_t(rows) * 4);
-        memcpy(code.enc_blob.data() + 16 + size_t(rows) * 4, lvl_off.data(), size_t(nl + 1) * 2);
+        code.enc_entries = entries;
+        code.enc_lvl_off = lvl_off;
     }
     return LDPC_OK;
+}
+
+std::vector<uint8_t> make_enc_blob(const HostCode &code, int epw)
+{
+    std::vector<uint8_t> blob;
+    if (!code.triangular) return blob;
+    const int rows = code.m, nl = code.encode_levels;
+    const std::vector<uint32_t> &entries = code.enc_entries;
+    const std::vector<uint16_t> &lvl_off = code.enc_lvl_off;
+    // passes of the walk over the levels >= 2
+    std::vector<uint16_t> passes;
+    for (int l = 1; l < nl; l++)
+        for (int pos = lvl_off[l]; pos < lvl_off[l + 1]; pos += epw)
+            passes.push_back(uint16_t(pos | ((std::min(epw, lvl_off[l + 1] - pos) - 1) << 11)));
+    // records: the parity members of each row of level >= 2 (its diagonal excluded)
+    const int n1 = nl >= 2 ? int(lvl_off[1]) : rows;
+    const int nrec = rows - n1;
+    const uint64_t z = uint64_t(sched_zero_row(code.n));
+    std::vector<uint64_t> recs(static_cast<size_t>(nrec), 0);
+    for (int i = n1; i < n1 + nrec; i++) {
+        const int r = int(entries[i] >> 16);
+        uint64_t rec = 0;
+        int nd = 0;
+        for (int j = code.row_ptr[r]; j < code.row_ptr[r + 1] - 1; j++) {
+            const int c = code.col_idx[j];
+            if (c < code.k) continue;
+            if (nd < 5) rec |= uint64_t(c) << (12 * nd);
+            nd++;
+        }
+        for (int j = nd; j < 5; j++) rec |= z << (12 * j);
+        if (nd > 5) rec = z | (z << 12) | (z << 24) | (z << 36) | (z << 48) | (1ull << 63);   // full-row form: no member listed
+        recs[size_t(i - n1)] = rec;
+    }
+    const size_t pt_off = 16 + size_t(rows) * 4 + size_t(nl + 1) * 2;
+    const size_t rec_off = (pt_off + passes.size() * 2 + 7) & ~size_t(7);
+    blob.assign((rec_off + size_t(nrec) * 8 + 15) & ~size_t(15), 0);
+    uint32_t hdr[4] = {uint32_t(rows), uint32_t(nl) | (uint32_t(nrec) << 16), uint32_t(passes.size()) << 16, 0u};
+    memcpy(blob.data(), hdr, 16);
+    memcpy(blob.data() + 16, entries.data(), size_t(rows) * 4);
+    memcpy(blob.data() + 16 + size_t(rows) * 4, lvl_off.data(), size_t(nl + 1) * 2);
+    if (!passes.empty()) memcpy(blob.data() + pt_off, passes.data(), passes.size() * 2);
+    if (nrec) memcpy(blob.data() + rec_off, recs.data(), size_t(nrec) * 8);
+    return blob;
 }
 
 }  // namespace ldpc

@@ -27,16 +27,32 @@ struct HostCode {
     int VW = 0;                     // u16 entries per variable row (4 or 8 ...), pad 0xFFFF
     std::vector<uint16_t> cidx;     // [m][RW]
     std::vector<uint16_t> vadj;     // [n][VW]
-    // static encode schedule blob (same format the peel compiler emits per codeword)
-    std::vector<uint8_t> enc_blob;
+    // static encode schedule (same form the peel compiler emits per codeword): entries sorted by level + level offsets
+    std::vector<uint32_t> enc_entries;   // (k + r) | r << 16
+    std::vector<uint16_t> enc_lvl_off;   // [encode_levels + 1]
 };
 
-// Schedule blob: u32 hdr[4] = {n_entries, n_levels, info0, info1}; u32 entries[n_entries]
-// (variable | check << 16) sorted by level; u16 lvl_off[n_levels + 1]; padded to 16 bytes.
-inline int sched_blob_max_bytes(int m)
+// Schedule blob: u32 hdr[4] = {n_entries, n_levels | n_records << 16, info0 | n_passes << 16, info1}; u32
+// entries[n_entries] (variable | check << 16) sorted by level; u16 lvl_off[n_levels + 1]; u16 passes[n_passes]: the
+// executor's walk over the levels >= 2 cut into passes of at most `epw` entries of ONE level, first entry | (count - 1)
+// << 11; padded to 8 bytes; u64 records[n_records], one per entry of level >= 2 in entry order: the entry's PRODUCED
+// members (members of its check that earlier entries produce) as 5 x 12-bit symbol indices (padding = the executor's
+// zero row), bit 63 = more than 5 (none listed); padded to 16 bytes.  n_records may be less than the number of such
+// entries (the executor then applies the rest in full-row form).  The peel kernel writes hdr, entries and lvl_off;
+// sched_records_kernel adds passes and records.
+inline int sched_blob_base_bytes(int m)      // without records
 {
-    int b = 16 + 4 * m + 2 * (m + 1);
-    return (b + 15) & ~15;
+    return (16 + 4 * m + 2 * (m + 1) + 2 * m + 7) & ~7;
+}
+inline int sched_blob_max_bytes(int m)       // with a record per entry
+{
+    return (sched_blob_base_bytes(m) + 8 * m + 15) & ~15;
+}
+constexpr int kSchedMaxRow = 4095;           // 12-bit symbol indices in the records
+inline int sched_zero_row(int n)             // the executor's all-zero row: behind its 256-row boxes, or (n > 3840) row 4095
+{
+    const int z = ((n + 255) / 256) * 256;
+    return z < kSchedMaxRow ? z : kSchedMaxRow;
 }
 
 // Returns 0 or a negative LDPC_ERR_* code; `err` receives a description.
@@ -44,5 +60,7 @@ int load_mat_sparse(const std::string &path, const char *var_name, int &rows, in
                     std::vector<int32_t> &col_ptr, std::vector<int32_t> &row_idx, std::string &err);
 int build_code(int rows, int cols, const std::vector<int32_t> &col_ptr,
                const std::vector<int32_t> &row_idx, HostCode &code, std::string &err);
+// The encoder's static schedule as a blob, its walk cut into passes of `epw` entries (empty if H is not triangular).
+std::vector<uint8_t> make_enc_blob(const HostCode &code, int epw);
 
 }  // namespace ldpc

@@ -26,6 +26,7 @@
 #include "payload_exec.cuh"
 #include "peel_schedule.cuh"
 #include "rs_gf256.cuh"
+#include "sched_records.cuh"
 
 using namespace ldpc;
 
@@ -73,14 +74,6 @@ static int ge_stage_mask() { const char *e = getenv("LDPC_CUDA_GE_STAGES"); retu
 
 // LDPC_CUDA_TMA4=0: the executor moves its slots box by box (3-D tensor copies only)
 static const bool g_tma4 = [] { const char *e = getenv("LDPC_CUDA_TMA4"); return !(e && *e == '0'); }();
-
-// LDPC_CUDA_EXEC_WIDE_MIN: executor levels with more entries than this are spread over a group's four warps (default:
-// what one warp covers in one pass); smaller levels are walked by one warp alone
-static int exec_wide_min(int entries_per_warp_pass)
-{
-    static const int forced = [] { const char *e = getenv("LDPC_CUDA_EXEC_WIDE_MIN"); return e && *e ? atoi(e) : -1; }();
-    return forced >= 0 ? forced : entries_per_warp_pass;
-}
 
 // LDPC_CUDA_DEBUG_SYNC=1: synchronise after every launch so that a faulting kernel is named
 static int debug_sync(const char *what, cudaStream_t st)
@@ -174,6 +167,7 @@ struct ldpc_ctx {
     int NW = 0, MW = 0, sched_stride = 0;
     // device tables
     uint16_t *d_cidx = nullptr, *d_vadj = nullptr;
+    uint16_t *d_rows_dec = nullptr, *d_rows_enc = nullptr;   // check rows arranged for the executor's decode / encode geometry
     uint8_t *d_enc_blob = nullptr;
     // scratch
     uint8_t *d_sched = nullptr;
@@ -214,7 +208,7 @@ struct ldpc_ctx {
     bool prof_on = false;
     struct ProfRec { cudaEvent_t a, b; int kind; };
     std::vector<ProfRec> prof_recs;
-    long long launches[LDPC_K_KINDS] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long launches[LDPC_K_KINDS] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 // brackets one kernel launch with events when profiling is on; always counts the launch
@@ -270,31 +264,89 @@ static std::string codes_dir()
 
 static int choose_geom(const ldpc_ctx *c, bool dynamic_sched, ExecGeom *g)
 {
-    const int n = c->code.n, S = c->S;
-    const int cidx_bytes = c->code.m * c->code.RW * 2;
-    const int blob = sched_blob_max_bytes(c->code.m);
+    const int n = c->code.n, S = c->S, m = c->code.m;
+    const int nbox = (n + kBoxRows - 1) / kBoxRows;
+    const int cidx_bytes = m * c->code.RW * 2;
     const int mask_bytes = dynamic_sched ? kExecMaxGroups * ((c->NW + 3) & ~3) * 4 : 0;   // hybrid mode: one mask per slot
-    const int fixed = cidx_bytes + 64 + 64 + mask_bytes + 1024;   // check rows, barriers, mailboxes, masks, base alignment
+    const int fixed = cidx_bytes + mask_bytes + 64 + 128 + 128;   // check rows, masks, barriers, mailboxes, base alignment
+    // a blob in shared memory: the static schedule whole; a per-codeword schedule with at least 64 records and, if
+    // there is room, one per check (the peel kernel emits what fits, entries past that take the full-row form)
     ExecGeom best;
     for (int W = 64; W >= 16; W >>= 1) {         // instantiated slice widths; S is a multiple of 16, so 16 always divides
         if (W > S || S % W) continue;
         if (c->force_W && W != c->force_W) continue;
-        const int slot = ((n + kBoxRows - 1) / kBoxRows) * kBoxRows * W + kExecZeroRowBytes;
+        const int slot = nbox * kBoxRows * W + kExecZeroRowBytes;
         if ((slot - kExecZeroRowBytes) / 16 > 0xFFFF) continue;   // check rows are staged as 16-bit offsets in 16-byte units
+        const int blob_min = dynamic_sched ? ((sched_blob_base_bytes(m) + 8 * std::min(m, 64) + 15) & ~15)
+                                           : int(make_enc_blob(c->code, 32 / (W / 16)).size());
+        const int blob_max = dynamic_sched ? sched_blob_max_bytes(m) : blob_min;
         int nslot;
-        if (dynamic_sched) nslot = (c->smem_optin - fixed) / (slot + blob);
-        else nslot = (c->smem_optin - fixed - blob) / slot;
+        if (dynamic_sched) nslot = (c->smem_optin - fixed) / (slot + blob_min);
+        else nslot = (c->smem_optin - fixed - blob_min) / slot;
         nslot = std::min(nslot, kExecMaxGroups);
         if (c->force_slots) nslot = std::min(nslot, c->force_slots);
         if (nslot < 1) continue;
+        int blob = blob_min;
+        if (dynamic_sched) blob = std::min(blob_max, ((c->smem_optin - fixed - nslot * slot) / nslot) & ~15);
         ExecGeom cand;
         cand.W = W; cand.nslot = nslot; cand.slot_bytes = slot; cand.sched_area = blob;
-        cand.smem_bytes = nslot * slot + (dynamic_sched ? nslot : 1) * blob + cidx_bytes + 64 + 64 + mask_bytes;
+        cand.smem_bytes = nslot * slot + (dynamic_sched ? nslot : 1) * blob + cidx_bytes + mask_bytes + 64 + 128;
         if (!best.W || (best.nslot < 3 && cand.nslot > best.nslot)) best = cand;
         if (best.nslot >= 3) break;
     }
     if (!best.W) return fail(LDPC_ERR_UNSUPPORTED, "code too long for one shared-memory slot (n * 16 bytes must fit)");
     *g = best;
+    return LDPC_OK;
+}
+
+// Check rows as the executor stages them (payload_exec.cuh, "Bank conflicts"): 16-bit offsets in 16-byte units from the
+// slot base; the RW slots of a row form 128 / W groups, group a holding the members u with u mod (128 / W) == a (its
+// bank class) as far as they fit, the rest in whatever slot is free; empty slots point at the zero row of their class
+// behind the slot's boxes.
+static int upload_exec_rows(ldpc_ctx *c, int W, uint16_t **d_rows)
+{
+    const HostCode &code = c->code;
+    const int SL = code.RW, NCLS = 128 / W, GS = SL / NCLS, LPG = W / 16;
+    const int zbase = ((code.n + kBoxRows - 1) / kBoxRows) * kBoxRows;
+    std::vector<uint16_t> rows(size_t(code.m) * SL);
+    std::vector<int> slot(static_cast<size_t>(SL));
+    for (int r = 0; r < code.m; r++) {
+        std::fill(slot.begin(), slot.end(), -1);
+        std::vector<int> spill;
+        for (int j = code.row_ptr[r]; j < code.row_ptr[r + 1]; j++) {
+            const int u = code.col_idx[j], a = u % NCLS;
+            int t = a * GS;
+            while (t < (a + 1) * GS && slot[size_t(t)] >= 0) t++;
+            if (t < (a + 1) * GS) slot[size_t(t)] = u; else spill.push_back(u);
+        }
+        for (int u : spill) {
+            int t = 0;
+            while (slot[size_t(t)] >= 0) t++;          // (a row has at most RW members)
+            slot[size_t(t)] = u;
+        }
+        for (int t = 0; t < SL; t++)
+            rows[size_t(r) * SL + t] = uint16_t((slot[size_t(t)] >= 0 ? slot[size_t(t)] : zbase + t / GS) * LPG);
+    }
+    cudaFree(*d_rows);
+    *d_rows = nullptr;
+    CUDA_TRY(cudaMalloc(d_rows, rows.size() * 2));
+    CUDA_TRY(cudaMemcpy(*d_rows, rows.data(), rows.size() * 2, cudaMemcpyHostToDevice));
+    return LDPC_OK;
+}
+
+// everything on the device that depends on the executor's geometry: the arranged check rows and the encoder's blob
+static int upload_geometry_tables(ldpc_ctx *c)
+{
+    int rc = upload_exec_rows(c, c->dec.W, &c->d_rows_dec);
+    if (!rc) rc = upload_exec_rows(c, c->enc.W, &c->d_rows_enc);
+    if (rc) return rc;
+    cudaFree(c->d_enc_blob);
+    c->d_enc_blob = nullptr;
+    if (c->code.triangular) {
+        const std::vector<uint8_t> blob = make_enc_blob(c->code, 32 / (c->enc.W / 16));
+        CUDA_TRY(cudaMalloc(&c->d_enc_blob, blob.size()));
+        CUDA_TRY(cudaMemcpy(c->d_enc_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+    }
     return LDPC_OK;
 }
 
@@ -304,7 +356,7 @@ static void free_ctx(ldpc_ctx *c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaFree(c->d_cidx); cudaFree(c->d_vadj); cudaFree(c->d_enc_blob); cudaFree(c->d_sched);
+    cudaFree(c->d_cidx); cudaFree(c->d_vadj); cudaFree(c->d_rows_dec); cudaFree(c->d_rows_enc); cudaFree(c->d_enc_blob); cudaFree(c->d_sched);
     cudaFree(c->d_work_ctr);
     cudaFree(c->d_sched2); cudaFree(c->d_sched_len2); cudaFree(c->d_resid2); cudaFree(c->d_fail_scratch2); cudaFree(c->d_work_ctr2);
     for (int i = 0; i < 2; i++) {
@@ -414,10 +466,6 @@ extern "C" int ldpc_ctx_create(ldpc_ctx **out, const char *h_mat_path, int code_
     CTX_TRY(cudaMemcpy(c->d_cidx, c->code.cidx.data(), c->code.cidx.size() * 2, cudaMemcpyHostToDevice));
     CTX_TRY(cudaMalloc(&c->d_vadj, c->code.vadj.size() * 2));
     CTX_TRY(cudaMemcpy(c->d_vadj, c->code.vadj.data(), c->code.vadj.size() * 2, cudaMemcpyHostToDevice));
-    if (c->code.triangular) {
-        CTX_TRY(cudaMalloc(&c->d_enc_blob, c->code.enc_blob.size()));
-        CTX_TRY(cudaMemcpy(c->d_enc_blob, c->code.enc_blob.data(), c->code.enc_blob.size(), cudaMemcpyHostToDevice));
-    }
     CTX_TRY(cudaMalloc(&c->d_sched, size_t(max_batch) * c->sched_stride));
     CTX_TRY(cudaMalloc(&c->d_sched_len, size_t(max_batch) * 4));
     CTX_TRY(cudaMalloc(&c->d_resid, size_t(max_batch) * 4));
@@ -435,6 +483,7 @@ extern "C" int ldpc_ctx_create(ldpc_ctx **out, const char *h_mat_path, int code_
     rc = choose_geom(c, true, &c->dec);
     if (!rc) rc = choose_geom(c, false, &c->enc);
     if (!rc) rc = setup_peel(c);
+    if (!rc) rc = upload_geometry_tables(c);
     if (rc) { free_ctx(c); return rc; }
     *out = c;
     return LDPC_OK;
@@ -494,7 +543,8 @@ extern "C" int ldpc_ctx_set_exec_geometry(ldpc_ctx *c, int slice_bytes, int slot
     if (!rc) rc = choose_geom(c, false, &e);
     if (rc) { c->force_W = oldW; c->force_slots = olds; return rc; }
     c->dec = d; c->enc = e;
-    return LDPC_OK;
+    CUDA_TRY(cudaSetDevice(c->device));
+    return upload_geometry_tables(c);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -542,11 +592,11 @@ static int launch_exec(ldpc_ctx *c, const ExecGeom &g, const void *d_in, int row
     if (nfull_out) { rc = cached_map(c, &out4_map, d_out, rows_out, B, g.W, nfull_out, false); if (rc) return rc; }
     ExecParams p;
     p.synd = d_synd; p.mask = d_mask; p.NW = c->NW; p.nfull_in = nfull_in; p.nfull_out = nfull_out;
-    p.cidx = c->d_cidx; p.sched = sched; p.sched_len = sched_len; p.B = B; p.sched_stride = sched_stride;
+    p.rows = sched_stride ? c->d_rows_dec : c->d_rows_enc; p.sched = sched; p.sched_len = sched_len; p.B = B; p.sched_stride = sched_stride;
     p.sched_max = g.sched_area; p.m = c->code.m; p.RW = c->code.RW; p.rows_in = rows_in; p.rows_out = rows_out;
     p.nbox_in = (rows_in + kBoxRows - 1) / kBoxRows; p.nbox_out = (rows_out + kBoxRows - 1) / kBoxRows;
     p.slices = c->S / g.W; p.nslot = g.nslot; p.slot_bytes = g.slot_bytes;
-    p.wide_min = exec_wide_min(32 / (g.W / 16));
+    p.zrow = sched_zero_row(c->code.n); p.out = static_cast<uint8_t *>(d_out); p.S = c->S;
     p.phase_cycles = sched_stride ? c->d_phase : nullptr;
     int rwm = 0;
     ExecKernel k = pick_exec(g.W, c->code.max_row_weight, &rwm);
@@ -791,6 +841,28 @@ static int decode_chunk(ldpc_ctx *c, const uint8_t *d_cw, const uint32_t *d_mask
     { int rcd = debug_sync("peel_schedule_kernel", st); if (rcd) return rcd; }
     const bool pattern_only = d_cw == nullptr;   // error-rate run: no payload
     if (!pattern_only) {
+        // records of the produced members, for the executor's level walk
+        RecParams rp;
+        rp.mask = d_mask; rp.sched = sched; rp.sched_len = sched_len; rp.cidx = c->d_cidx; rp.B = B; rp.n = c->code.n; rp.m = c->code.m;
+        rp.RW = c->code.RW; rp.NW = c->NW; rp.stride = c->sched_stride; rp.blob_cap = c->dec.sched_area; rp.zrow = sched_zero_row(c->code.n); rp.epw = 32 / (c->dec.W / 16);
+        const int rsmem = c->code.m * c->code.RW * 2 + kRecWarps * ((c->NW + 1 + 3) & ~3) * 4;
+        const int rgrid = int(std::min<long long>((B + kRecWarps - 1) / kRecWarps, (long long)c->num_sms * 8));
+        typedef void (*RecKernel)(const RecParams);
+        RecKernel rk = nullptr;
+        switch (c->code.RW / 8) {
+            case 1: rk = sched_records_kernel<1>; break;
+            case 2: rk = sched_records_kernel<2>; break;
+            case 3: rk = sched_records_kernel<3>; break;
+            case 4: rk = sched_records_kernel<4>; break;
+            default: return fail(LDPC_ERR_UNSUPPORTED, "row weight above 32");
+        }
+        if (rsmem > 48 * 1024) { int rcs = allow_max_smem(reinterpret_cast<const void *>(rk), c->smem_optin); if (rcs) return rcs; }
+        {
+            ProfScope ps(c, LDPC_K_RECORDS, st);
+            rk<<<rgrid, kRecWarps * 32, rsmem, st>>>(rp);
+        }
+        CUDA_TRY(cudaGetLastError());
+        { int rcd = debug_sync("sched_records_kernel", st); if (rcd) return rcd; }
         int rc = launch_exec(c, c->dec, d_cw, c->code.n, d_out, c->code.k, sched, sched_len, c->sched_stride, B, st,
                              mode == LDPC_MODE_HYBRID ? c->hyb.d_synd : nullptr, d_mask);
         if (rc) return rc;

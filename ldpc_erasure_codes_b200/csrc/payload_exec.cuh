@@ -15,23 +15,36 @@
 // group owns one shared-memory slot and cycles
 //     TMA load (cp.async.bulk.tensor, 3-D / 4-D map over [B][rows][S], + the schedule blob as a
 //               1-D bulk copy, all completing on the slot's mbarrier)
-//  -> XOR the schedule into the slot, level by level
+//  -> XOR the schedule into the slot
 //  -> TMA store of the first rows_out rows.
-// HBM traffic is exactly the algorithmic bytes (+ the schedule blob): every input byte is read
-// once and every output byte written once by TMA; all gathers hit shared memory.
+// HBM traffic is exactly the algorithmic bytes (+ the schedule blob and the erasure mask): every
+// input byte is read once and every output byte written once by TMA; all gathers hit shared memory.
 //
-// The level walk.  At the code's threshold a schedule is a LONG chain of SMALL levels ((2040,1530) at
-// 20 % erasures: ~330 entries in ~20 levels -- 80, 40, 25, 19, 15 entries, then ~10 per level), so the
-// XOR phase is a chain of shared-memory round trips, not a bandwidth problem.  Its link is kept short:
-//   * the rows a schedule produces are zeroed first and every member of the check is gathered,
-//     the target included (the reference does the same: erased symbols are zero and XORed in,
-//     ldpc_erasure_decoder.cl:17-20,68-75): no per-member compare/select;
-//   * check rows are staged once per CTA as pre-scaled 16-byte offsets, row padding pointing at a
-//     zero row behind the slot: a member's address is one shift-add;
-//   * a level of more than `wide_min` entries is spread over the group's four warps and closed by the
-//     group's named barrier; a run of smaller levels is walked by ONE warp alone, in program
-//     order, with only __syncwarp() between levels -- no inter-warp hand-off on the chain -- while
-//     the entry word and check row of the next pass are fetched ahead of the current pass's gathers.
+// The XOR phase.  At the code's threshold a schedule is a LONG chain of SMALL levels ((2040,1530) at
+// 20 % erasures: ~330 entries in ~24 levels -- 80, 40, 25, 19, 15 entries, then ~10 per level).  Walking
+// that chain with one full check-row gather (14 shared-memory loads, XOR tree, store: ~400 cycles) per
+// level made the phase a latency chain of ~10-17 k cycles per unit.  It is split instead:
+//   1. BULK, dependency free, all four warps of the group: the rows the schedule produces are zeroed,
+//      then every entry gathers ALL members of its check (the reference does the same: erased symbols are
+//      zero and XORed in, ldpc_erasure_decoder.cl:17-20,68-75) -- which yields s_i = XOR of the check's
+//      RECEIVED members -- and stores s_i into its target row.
+//      Rounds run from the highest level down: an entry never reads the target of an entry of the same
+//      or a higher level, so a round's stores cannot disturb a later round's gathers.
+//   2. WALK: entry i of level >= 2 is  row[v_i] = s_i ^ XOR of its PRODUCED members (erased originally,
+//      recovered at a lower level: ~2.6 per entry at 20 %), which the schedule lists in an 8-byte record
+//      per entry (sched_records.cuh; hmat.cpp for the encoder): 6 loads and one store per pass of <= 32 / LPG
+//      entries of one level.  A warp issues in order and a pass is ~90 instructions with its bookkeeping
+//      (which entries, entry word, record, addresses), so the passes rotate over the group's four warps:
+//      the passes are listed in the blob; warp p % 4 prepares pass p while the three passes before it run, waits for pass p-1 on a named
+//      barrier (bar.sync / bar.arrive between two warps), then only loads, XORs, stores and signals.
+//      The link of the chain is one shared-memory round trip plus the hand-off.  Idle lanes rewrite a
+//      zero row.  Entries with more than five produced members (1 %), or past the records the blob
+//      holds, take the full-row form row[v] ^= XOR of all members (the target itself cancels).
+// Bank conflicts.  A row of W bytes covers W / 4 of the 32 banks: rows u, u' collide iff u = u' mod 128 / W
+// (their "class").  A 128-bit shared load is served a quarter warp at a time, i.e. 128 / W entries together:
+// the host arranges every check row in 128 / W groups of slots, group a holding the members of class a, and
+// entry j of a quarter warp reads its row's groups rotated by j (a rotated ADDRESS, static registers), so at
+// every step the entries of a quarter warp gather from different classes.
 // The other groups of the CTA run other units at other phases and keep TMA traffic flowing.
 #pragma once
 #include "device_utils.cuh"
@@ -39,12 +52,13 @@
 namespace ldpc {
 
 constexpr int kExecWarpsPerGroup = 4;
-constexpr int kExecMaxGroups = 4;
+constexpr int kExecMaxGroups = 3;      // named barriers: 1 + g per group, 4 + 4 g + w for the walk's hand-offs (16 in all)
 constexpr int kBoxRows = 256;
-constexpr int kExecZeroRowBytes = 128;   // behind every slot: what row padding reads
+constexpr int kExecZeroRowBytes = 128;   // behind every slot: what row padding reads, one 16..64-byte zero row per bank class
+constexpr int kExecBulkRound = 4;        // entries a thread gathers between two barriers of the bulk phase
 
 struct ExecParams {
-    const uint16_t *cidx;       // [m][RW] check rows, pad 0xFFFF
+    const uint16_t *rows;       // [m][RW] check rows arranged for this geometry (ldpc_cuda.cu: build_exec_rows): 16-byte offsets into a slot
     const uint8_t *sched;       // per-codeword blobs (stride sched_stride) or one static blob
     const uint32_t *sched_len;  // [B] blob bytes, nullptr for a static schedule
     long long B;                // codewords in this launch
@@ -56,12 +70,14 @@ struct ExecParams {
     int slices;                 // S / W
     int nslot;                  // = number of warp groups
     int slot_bytes;             // shared bytes per slot (payload rows + the zero row)
-    int wide_min;               // levels with more entries than this are spread over the group's warps
+    int zrow;                   // row index of the all-zero row inside a slot (sched_zero_row)
     uint8_t *synd;              // hybrid mode: [B][m][S] check syndromes of the codewords that still have erasures, or nullptr
     const uint32_t *mask;       // hybrid mode: [B][NW] erasure masks (erased rows are zeroed in the slot before the XOR phase)
     int NW;
+    uint8_t *out;               // [B][rows_out][S]: the output the tensor maps describe (the walk's symbols are re-stored with plain stores)
+    int S;
     int nfull_in, nfull_out;    // whole 256-row boxes moved by ONE 4-D tensor copy (map [B][rows/256][256][S]); the rest box by box
-    unsigned long long *phase_cycles;  // tuning aid (nullptr = off): [0] claim+issue, [1] load wait, [2] XOR, [3] store, [4] units
+    unsigned long long *phase_cycles;  // tuning aid (nullptr = off): [0] claim+issue, [1] load wait, [2] level walk, [3] store, [4] units, [5] zeroing + bulk gather, [6] walk passes
 };
 
 __device__ __forceinline__ void xor_acc(uint4 &a, const uint4 v)
@@ -87,40 +103,80 @@ payload_exec_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
 {
     constexpr int RWQ = (RWM + 7) / 8;                // uint4 chunks of a padded check row
     constexpr int LPG = W / 16;                       // lanes per entry
+    constexpr int LPG_SH = LPG == 1 ? 0 : (LPG == 2 ? 1 : 2);
+    constexpr int W_SH = LPG_SH + 4;                  // log2(W)
     constexpr int GT = kExecWarpsPerGroup * 32;       // threads per group
     constexpr int NGROUPS = GT / LPG;                 // entries a group handles per pass
-    constexpr int EPW = 32 / LPG;                     // entries per warp and pass
-    constexpr int WPGc = kExecWarpsPerGroup;
-    extern __shared__ __align__(1024) uint8_t smem[];
-    // layout: [slots][blobs: nslot (dynamic) or 1 (static)][check rows][barriers][unit mailboxes][masks (hybrid)]
+    constexpr int R = kExecBulkRound;
+    extern __shared__ __align__(128) uint8_t smem[];
+    // layout: [slots][blobs: nslot (per-codeword schedules) or 1 (static)][check rows][masks (hybrid)][barriers][unit mailboxes]
+    const bool dynamic = p.sched_stride != 0;
     uint8_t *slots = smem;
     uint8_t *blobs = slots + size_t(p.nslot) * p.slot_bytes;
-    const bool dynamic = p.sched_stride != 0;
     uint16_t *cidx_s = reinterpret_cast<uint16_t *>(blobs + size_t(dynamic ? p.nslot : 1) * p.sched_max);
-    uint64_t *full = reinterpret_cast<uint64_t *>(cidx_s + size_t(p.m) * (RWQ * 8));   // [nslot]
+    uint32_t *masks = reinterpret_cast<uint32_t *>(cidx_s + size_t(p.m) * (RWQ * 8));
+    const int msk_words = p.synd ? ((p.NW + 3) & ~3) : 0;
+    uint64_t *full = reinterpret_cast<uint64_t *>(masks + size_t(p.nslot) * msk_words);   // [nslot]
     int *mailbox = reinterpret_cast<int *>(full + 8);        // [g] unit of group g, [8] next unit
-    uint32_t *msk_s = reinterpret_cast<uint32_t *>(mailbox + 16) + (threadIdx.x / GT) * ((p.NW + 3) & ~3);   // hybrid mode: the unit's mask
 
     const int g = threadIdx.x / GT;          // group = slot
     const int tg = threadIdx.x % GT;         // thread in group
     const bool leader = tg == 0;
-    const int zrow16 = (p.slot_bytes - kExecZeroRowBytes) / 16;   // the zero row, in 16-byte units from the slot base
+    uint32_t *msk_s = masks + g * msk_words;
+    const uint32_t cidx_a = smem_u32(cidx_s);
 
-    {   // stage the check rows once per CTA as 16-byte offsets into a slot (row u -> u * W / 16, padding -> the zero row)
-        const uint32_t *src = reinterpret_cast<const uint32_t *>(p.cidx);
-        uint32_t *dst = reinterpret_cast<uint32_t *>(cidx_s);
-        for (int i = threadIdx.x; i < p.m * RWQ * 4; i += blockDim.x) {
-            const uint32_t w = src[i];
-            const uint32_t lo = w & 0xFFFFu, hi = w >> 16;
-            dst[i] = (lo == 0xFFFFu ? uint32_t(zrow16) : lo * LPG) | ((hi == 0xFFFFu ? uint32_t(zrow16) : hi * LPG) << 16);
+    // a check row: SL slots in NCLS groups; my entry reads the groups rotated by its place in the quarter warp
+    constexpr int SL = RWQ * 8;                       // slots (16-bit offsets) per row
+    constexpr int NCLS = 128 / W;                     // bank classes = entries per quarter warp
+    constexpr int GS = SL / NCLS;                     // slots per group (1, 2, 4 or 8 -> 2 .. 16 bytes)
+    static_assert(GS >= 1 && GS * NCLS == SL, "row slots must split into one group per bank class");
+    const uint32_t rot = (uint32_t(threadIdx.x & 31) / LPG) % NCLS;
+    auto load_row = [&](uint32_t c, uint32_t (&rr)[RWQ * 4]) {   // rr: SL slots as packed pairs
+        const uint32_t row_a = cidx_a + c * (SL * 2);
+#pragma unroll
+        for (int a = 0; a < NCLS; a++) {
+            const uint32_t ga = row_a + ((uint32_t(a) + rot) % NCLS) * (GS * 2);
+            if (GS % 8 == 0) {
+#pragma unroll
+                for (int i = 0; i < GS / 8; i++) {
+                    const uint4 r4 = lds128(ga + 16 * i);
+                    const int w0 = (a * GS) / 2 + 4 * i;
+                    rr[w0 + 0] = r4.x; rr[w0 + 1] = r4.y; rr[w0 + 2] = r4.z; rr[w0 + 3] = r4.w;
+                }
+            } else if (GS % 4 == 0) {
+#pragma unroll
+                for (int i = 0; i < GS / 4; i++)
+                    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(rr[(a * GS) / 2 + 2 * i]), "=r"(rr[(a * GS) / 2 + 2 * i + 1]) : "r"(ga + 8 * i));
+            } else if (GS % 2 == 0) {
+#pragma unroll
+                for (int i = 0; i < GS / 2; i++)
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(rr[(a * GS) / 2 + i]) : "r"(ga + 4 * i));
+            } else {
+#pragma unroll
+                for (int i = 0; i < GS; i++) {
+                    const int t = a * GS + i;
+                    unsigned short h;
+                    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(ga + 2 * i));
+                    if (t & 1) rr[t >> 1] |= uint32_t(h) << 16; else rr[t >> 1] = h;
+                }
+            }
         }
+    };
+
+    {   // stage the arranged check rows once per CTA
+        const uint4 *src = reinterpret_cast<const uint4 *>(p.rows);
+        uint4 *dst = reinterpret_cast<uint4 *>(cidx_s);
+        for (int i = threadIdx.x; i < p.m * RWQ; i += blockDim.x) dst[i] = src[i];
         if (!dynamic) {
             const uint4 *s2 = reinterpret_cast<const uint4 *>(p.sched);
             uint4 *d2 = reinterpret_cast<uint4 *>(blobs);
             for (int i = threadIdx.x; i < p.sched_max / 16; i += blockDim.x) d2[i] = s2[i];
         }
-        for (int s = threadIdx.x / 8; s < p.nslot; s += blockDim.x / 8)      // the zero rows (never touched by TMA)
+        for (int s = threadIdx.x / 8; s < p.nslot; s += blockDim.x / 8) {     // the zero rows (no TMA load or entry ever writes them)
             reinterpret_cast<uint4 *>(slots + size_t(s + 1) * p.slot_bytes - kExecZeroRowBytes)[threadIdx.x % 8] = make_uint4(0u, 0u, 0u, 0u);
+            const size_t off = size_t(s) * p.slot_bytes + size_t(p.zrow) * W;      // (the records' zero row: the same place unless n > 3840)
+            if ((threadIdx.x % 8) * 16 < W) reinterpret_cast<uint4 *>(slots + off)[threadIdx.x % 8] = make_uint4(0u, 0u, 0u, 0u);
+        }
         if (threadIdx.x == 0) {
             for (int s = 0; s < p.nslot; s++) mbar_init(&full[s], 1);
             mailbox[8] = 0;
@@ -163,6 +219,7 @@ payload_exec_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
 
     const int wg = tg >> 5;                       // warp in group
     const int es = (tg & 31) / LPG;               // entry slot inside the warp
+    const int eslot = tg / LPG;                   // entry slot inside the group
 
     while (true) {
         // ---- leader: start the loads of the unit claimed earlier, claim the one after -----------
@@ -195,104 +252,143 @@ payload_exec_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
 
         const uint32_t *hdr = reinterpret_cast<const uint32_t *>(blob);
         const int ne = int(hdr[0]);
-        const int nl = int(hdr[1]);
+        const int nl = int(hdr[1] & 0xFFFFu), nrec = int(hdr[1] >> 16);
         const uint32_t *ent = hdr + 4;
         const uint16_t *lvo = reinterpret_cast<const uint16_t *>(ent + ne);
+        const int n1 = nl >= 2 ? int(lvo[1]) : ne;     // entries of the first level: no produced members, no record
         const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
-        if (p.synd && hdr[2] != 0u) {   // (uniform over the group)
+        const bool resid = p.synd && (hdr[2] & 0xFFFFu) != 0u;     // (uniform over the group)
+        if (resid) {
             // Hybrid mode, the codeword keeps erasures after peeling: symbols that stay unknown must read as
             // zero when the syndromes are formed below, so every erased row is zeroed (a superset of the rows
             // the schedule produces).
             named_bar_sync(bar_id, GT);   // the mask words
-            for (int u = tg / LPG; u < p.rows_in; u += NGROUPS)
+            for (int u = eslot; u < p.rows_in; u += NGROUPS)
                 if ((msk_s[u >> 5] >> (u & 31)) & 1u) sts128(base_a + u * W, z4);
         } else {
-            // the rows this schedule produces read as zero until they are written: every gather below takes
-            // ALL members of its check, the target included
-            for (int i = tg / LPG; i < ne; i += NGROUPS) sts128(base_a + (ent[i] & 0xFFFFu) * W, z4);
+            // the rows this schedule produces read as zero until they are written
+            for (int i = eslot; i < ne; i += NGROUPS) sts128(base_a + ((ent[i] & 0xFFFFu) << W_SH), z4);
         }
         named_bar_sync(bar_id, GT);
 
-        // ---- XOR the schedule into the slot -----------------------------------------------
-        struct Prep { uint32_t e; uint32_t rr[RWQ * 4]; };
-        auto fetch = [&](int idx, bool valid) -> Prep {   // entry word + its check row (payload independent)
-            Prep q;
-            q.e = valid ? ent[idx] : 0u;
-            const uint4 *row = reinterpret_cast<const uint4 *>(cidx_s + size_t(q.e >> 16) * (RWQ * 8));
+        // ---- 1. bulk: s_i = XOR of the check's received members, records of the produced ones --------
+        for (int hi = ne; hi > 0; hi -= R * NGROUPS) {
+            uint4 res[R];
+            uint32_t va[R];
 #pragma unroll
-            for (int qq = 0; qq < RWQ; qq++) {
-                const uint4 r4 = row[qq];
-                q.rr[qq * 4 + 0] = r4.x; q.rr[qq * 4 + 1] = r4.y; q.rr[qq * 4 + 2] = r4.z; q.rr[qq * 4 + 3] = r4.w;
+            for (int q = 0; q < R; q++) {
+                const int idx = hi - 1 - (q * NGROUPS + eslot);
+                va[q] = 0u;
+                res[q] = z4;
+                if (idx >= 0) {
+                    const uint32_t e = ent[idx];
+                    uint32_t rr[RWQ * 4];
+                    load_row(e >> 16, rr);
+                    uint4 val[SL];
+#pragma unroll
+                    for (int t = 0; t < SL; t++) {
+                        const uint32_t o16 = (t & 1) ? (rr[t >> 1] >> 16) : (rr[t >> 1] & 0xFFFFu);
+                        val[t] = lds128(base_a + (o16 << 4));
+                    }
+#pragma unroll
+                    for (int st = 1; st < SL; st <<= 1)
+#pragma unroll
+                        for (int t = 0; t + st < SL; t += 2 * st) xor_acc(val[t], val[t + st]);
+                    res[q] = val[0];
+                    va[q] = base_a + ((e & 0xFFFFu) << W_SH);
+                }
             }
-            return q;
-        };
-        auto apply = [&](const Prep &q) {                 // gather every member, XOR tree, store the symbol
-            uint4 val[RWM];
+            named_bar_sync(bar_id, GT);     // every gather of the round is done
 #pragma unroll
-            for (int t = 0; t < RWM; t++) {
-                const uint32_t o16 = (t & 1) ? (q.rr[t >> 1] >> 16) : (q.rr[t >> 1] & 0xFFFFu);
-                val[t] = lds128(base_a + (o16 << 4));
-            }
-#pragma unroll
-            for (int st = 1; st < RWM; st <<= 1)
-#pragma unroll
-                for (int t = 0; t + st < RWM; t += 2 * st) xor_acc(val[t], val[t + st]);
-            sts128(base_a + (q.e & 0xFFFFu) * W, val[0]);
-        };
+            for (int q = 0; q < R; q++)
+                if (va[q]) sts128(va[q], res[q]);
+        }
+        fence_proxy_async_smem();           // my writes to the slot -> visible to the TMA store below
+        named_bar_sync(bar_id, GT);
+        if (p.phase_cycles) lap(5);
+        // Every symbol the schedule does not produce, and every symbol of the first level, is final: the first
+        // rows_out rows go out NOW, while the level walk runs; the symbols the walk produces (holding s_i, or whatever the
+        // asynchronous read catches) are stored again below, after this store has completed.
+        if (leader) {
+            const long long b = blockIdx.x + (long long)(j / p.slices) * gridDim.x;
+            const int sl = j % p.slices;
+            if (p.nfull_out) tma_store_4d(&out4_map, slot, sl * W, 0, 0, int(b));
+            for (int q = p.nfull_out; q < p.nbox_out; q++)
+                tma_store_3d(&out_map, slot + size_t(q) * kBoxRows * W, sl * W, q * kBoxRows, int(b));
+            bulk_commit();
+        }
 
-        int L = 0;
-        bool in_step = true;          // all warps of the group are at the same point of the walk
-        while (L < nl) {
-            const int s0 = lvo[L], s1 = lvo[L + 1];
-            if (s1 - s0 > p.wide_min) {
-                // a wide level: my warp takes entries s0 + wg * EPW + es, + 4 * EPW, ...
-                if (!in_step) named_bar_sync(bar_id, GT);           // warp 0 has finished the small levels below
-                int idx = s0 + wg * EPW + es;
-                Prep cur = fetch(idx, idx < s1);
-                for (int base = s0 + wg * EPW; base < s1; base += WPGc * EPW) {
-                    const bool valid = idx < s1;
-                    const int nidx = idx + WPGc * EPW;
-                    const Prep nxt = fetch(nidx, nidx < s1);
-                    if (valid) apply(cur);
-                    cur = nxt;
-                    idx = nidx;
-                }
-                named_bar_sync(bar_id, GT);
-                in_step = true;
-                L++;
-            } else {
-                // a run of small levels [L, L2): warp 0 walks it alone in program order
-                int L2 = L + 1, e2 = s1;
-                while (L2 < nl) {
-                    const int nx = lvo[L2 + 1];
-                    if (nx - e2 > p.wide_min) break;
-                    e2 = nx;
-                    L2++;
-                }
-                if (wg == 0) {
-                    int lv = L, lend = s1;              // current level and its end
-                    int pos = s0;                       // first entry of the current pass
-                    Prep cur = fetch(pos + es, pos + es < lend);
-                    bool cur_valid = pos + es < lend;
-                    while (true) {
-                        // next pass: the rest of this level, or the start of the next one
-                        int npos = pos + EPW, nlv = lv, nlend = lend;
-                        if (npos >= lend) { npos = lend; nlv = lv + 1; if (nlv < L2) nlend = lvo[nlv + 1]; }
-                        const bool more = nlv < L2;
-                        const bool nvalid = more && npos + es < nlend;
-                        const Prep nxt = fetch(npos + es, nvalid);
-                        if (cur_valid) apply(cur);
-                        __syncwarp();                   // this pass's symbols are visible to the warp's next gathers
-                        if (!more) break;
-                        cur = nxt; cur_valid = nvalid; pos = npos; lv = nlv; lend = nlend;
+        // ---- 2. walk the levels >= 2: pass p (<= EPW entries of one level, listed in the blob) belongs to warp p % 4 ----
+        const int npass = int(hdr[2] >> 16);
+        if (npass > 0) {
+            const uint32_t z = uint32_t(p.zrow);
+            const uint32_t zlo = z | (z << 12) | (z << 24), zhi = (z >> 8) | (z << 4) | (z << 16);
+            const uint32_t ent_a = smem_u32(ent);
+            const uint32_t pt_a = smem_u32(lvo) + 2u * uint32_t(nl + 1);
+            const uint32_t rec_a = (pt_a + 2u * uint32_t(npass) + 7u) & ~7u;
+            const int hand_in = 4 + g * 4 + ((wg + 3) & 3), hand_out = 4 + g * 4 + wg;
+            uint32_t f_e, f_lo, f_hi;
+            auto fetch = [&](int pass) {       // entry word and record of my lane's entry in that pass
+                f_e = z; f_lo = zlo; f_hi = zhi;                   // an idle lane rewrites the zero row with zeros
+                if (pass < npass) {
+                    unsigned short pw;
+                    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(pw) : "r"(pt_a + 2u * uint32_t(pass)));
+                    const int idx = int(pw & 0x7FFu) + es;
+                    if (es <= int(pw >> 11)) {
+                        const int r = idx - n1;
+                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(f_e) : "r"(ent_a + 4u * uint32_t(idx)));
+                        if (r < nrec) asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(f_lo), "=r"(f_hi) : "r"(rec_a + 8u * uint32_t(r)));
+                        else f_hi |= 0x80000000u;                  // no record: full-row form
                     }
                 }
-                in_step = false;
-                L = L2;
+            };
+            fetch(wg);
+            unsigned long long mine = 0;
+            for (int pass = wg; pass < npass; pass += kExecWarpsPerGroup) {
+                const uint32_t e = f_e;
+                const uint32_t ta = base_a + ((e & 0xFFFu) << W_SH);
+                const uint32_t a0 = base_a + ((f_lo & 0xFFFu) << W_SH);
+                const uint32_t a1 = base_a + (((f_lo >> 12) & 0xFFFu) << W_SH);
+                const uint32_t a2 = base_a + ((((f_lo >> 24) | (f_hi << 8)) & 0xFFFu) << W_SH);
+                const uint32_t a3 = base_a + (((f_hi >> 4) & 0xFFFu) << W_SH);
+                const uint32_t a4 = base_a + (((f_hi >> 16) & 0xFFFu) << W_SH);
+                const bool slow = (f_hi >> 31) != 0u;
+                const bool any_slow = __any_sync(0xFFFFFFFFu, slow);
+                if (pass > 0) asm volatile("bar.sync %0, 64;" ::"r"(hand_in) : "memory");      // pass p-1 is in the slot
+                uint4 acc = lds128(ta);
+                const uint4 x0 = lds128(a0), x1 = lds128(a1), x2 = lds128(a2), x3 = lds128(a3), x4 = lds128(a4);
+                acc.x ^= x0.x ^ x1.x ^ x2.x ^ x3.x ^ x4.x;
+                acc.y ^= x0.y ^ x1.y ^ x2.y ^ x3.y ^ x4.y;
+                acc.z ^= x0.z ^ x1.z ^ x2.z ^ x3.z ^ x4.z;
+                acc.w ^= x0.w ^ x1.w ^ x2.w ^ x3.w ^ x4.w;
+                sts128(ta, acc);
+                if (any_slow) {
+                    if (slow) {
+                        // full-row form: b2 = s ^ (R ^ D ^ s) = R ^ D, with s = R = XOR of the received members (the
+                        // target row, one of the members) and D = XOR of the produced ones
+                        uint32_t rr[RWQ * 4];
+                        load_row(e >> 16, rr);
+                        uint4 b2 = acc;
+#pragma unroll
+                        for (int u = 0; u < SL; u++) {
+                            const uint32_t o16 = (u & 1) ? (rr[u >> 1] >> 16) : (rr[u >> 1] & 0xFFFFu);
+                            xor_acc(b2, lds128(base_a + (o16 << 4)));
+                        }
+                        sts128(ta, b2);
+                    }
+                    __syncwarp();
+                }
+                if (pass + 1 < npass) asm volatile("bar.arrive %0, 64;" ::"r"(hand_out) : "memory");   // my pass is in the slot
+                fetch(pass + kExecWarpsPerGroup);
+                mine++;
             }
+            if (p.phase_cycles && (tg & 31) == 0) atomicAdd(&p.phase_cycles[6], mine);
         }
-        // ---- store the first rows_out rows, recycle the slot --------------------------------
-        fence_proxy_async_smem();
+        // ---- the walk's symbols, recycle the slot --------------------------------
+        if (leader) {
+            if (npass > 0) bulk_wait_all0();    // the early store is complete: what follows overwrites it in global memory
+            else bulk_wait_read0();             // the slot's bytes are on their way to L2; it may be overwritten now
+        }
         named_bar_sync(bar_id, GT);
         lap(2);
         if (p.synd) {
@@ -300,20 +396,15 @@ payload_exec_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
             // members known NOW.  They are all in the slot, so the syndromes are formed here -- one level, no
             // chain -- instead of being gathered from HBM later.  Every member is XORed in: the symbols that
             // are still unknown were zeroed above.
-            if (hdr[2] != 0u) {
+            if (resid) {
                 const long long b = blockIdx.x + (long long)(j / p.slices) * gridDim.x;
                 uint8_t *dst = p.synd + (size_t(b) * p.m) * (size_t(p.slices) * W) + size_t(j % p.slices) * W + (tg % LPG) * 16;
-                for (int r = tg / LPG; r < p.m; r += NGROUPS) {
-                    const uint4 *row = reinterpret_cast<const uint4 *>(cidx_s + size_t(r) * (RWQ * 8));
+                for (int r = eslot; r < p.m; r += NGROUPS) {
                     uint32_t rr[RWQ * 4];
-#pragma unroll
-                    for (int qq = 0; qq < RWQ; qq++) {
-                        const uint4 r4 = row[qq];
-                        rr[qq * 4 + 0] = r4.x; rr[qq * 4 + 1] = r4.y; rr[qq * 4 + 2] = r4.z; rr[qq * 4 + 3] = r4.w;
-                    }
+                    load_row(uint32_t(r), rr);
                     uint4 acc = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-                    for (int t = 0; t < RWM; t++) {
+                    for (int t = 0; t < SL; t++) {
                         const uint32_t o16 = (t & 1) ? (rr[t >> 1] >> 16) : (rr[t >> 1] & 0xFFFFu);
                         xor_acc(acc, lds128(base_a + (o16 << 4)));
                     }
@@ -322,14 +413,14 @@ payload_exec_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
             }
             named_bar_sync(bar_id, GT);   // the slot is recycled by the leader below: every gather must be done
         }
-        if (leader) {
+        if (npass > 0) {
             const long long b = blockIdx.x + (long long)(j / p.slices) * gridDim.x;
-            const int sl = j % p.slices;
-            if (p.nfull_out) tma_store_4d(&out4_map, slot, sl * W, 0, 0, int(b));
-            for (int q = p.nfull_out; q < p.nbox_out; q++)
-                tma_store_3d(&out_map, slot + size_t(q) * kBoxRows * W, sl * W, q * kBoxRows, int(b));
-            bulk_commit();
-            bulk_wait_read0();   // the slot's bytes are on their way to L2; it may be overwritten now
+            uint8_t *dst = p.out + size_t(b) * p.rows_out * p.S + size_t(j % p.slices) * W + (tg % LPG) * 16;
+            for (int i = n1 + eslot; i < ne; i += NGROUPS) {
+                const uint32_t v = ent[i] & 0xFFFu;
+                if (int(v) < p.rows_out) *reinterpret_cast<uint4 *>(dst + size_t(v) * p.S) = lds128(base_a + (v << W_SH));
+            }
+            named_bar_sync(bar_id, GT);         // the slot is recycled by the leader: every read of it is done
         }
         lap(3);
         if (p.phase_cycles && leader) atomicAdd(&p.phase_cycles[4], 1ull);

@@ -34,7 +34,7 @@ for P in rates:
                  exec_GBs=round(alg / ex / 1e6, 1), fer=round(float(fail.float().mean()), 4))
         ph = pr.get("exec_phase_cycles", [0] * 8)
         if ph[4]:
-            r["phase_cyc_per_unit"] = dict(claim=ph[0] // ph[4], load=ph[1] // ph[4], xor=ph[2] // ph[4], store=ph[3] // ph[4])
+            r["phase_cyc_per_unit"] = dict(claim=ph[0] // ph[4], load=ph[1] // ph[4], bulk=ph[5] // ph[4], walk=ph[2] // ph[4], store=ph[3] // ph[4])
         print(json.dumps(r), flush=True); res.append(r)
 # encode
 for (W, slots) in geoms:
