@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define LDPC_CUDA_ABI_VERSION 3
+#define LDPC_CUDA_ABI_VERSION 2
 
 enum {
     LDPC_OK = 0,
@@ -204,8 +204,7 @@ enum { LDPC_K_PEEL = 0, LDPC_K_EXEC_DECODE = 1, LDPC_K_EXEC_ENCODE = 2,
        LDPC_K_HYBRID_WARP = 5,   /* stage 2: per-warp Gauss-Jordan on what stage 1 deferred (rare)          */
        LDPC_K_HYBRID_CTA = 6,    /* stage 3: CTA-per-codeword Gauss-Jordan on what stage 2 deferred         */
        LDPC_K_HYBRID_APPLY = 7,  /* stage 1, payload part: replay of the recorded pivots                    */
-       LDPC_K_RECORDS = 8,       /* schedule records for the executor's level walk (after the peel kernel)  */
-       LDPC_K_KINDS = 9 };
+       LDPC_K_KINDS = 8 };
 typedef struct ldpc_profile {
     double ms[LDPC_K_KINDS];        /* summed device time per kernel kind (profiling on)  */
     int64_t launches[LDPC_K_KINDS]; /* kernel launches per kind since create / last reset */

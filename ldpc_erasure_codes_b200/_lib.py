@@ -39,8 +39,8 @@ class Stats(C.Structure):
     _fields_ = [(n, C.c_int64) for n in ("frames", "ldpc_errors", "rs_errors", "ml_attempts", "ml_failures", "ml_recovered", "any_errors")]
 
 
-K_KINDS = 9
-KIND_NAMES = ["peel", "exec_decode", "exec_encode", "hybrid", "channel", "hybrid_warp", "hybrid_cta", "hybrid_apply", "records"]
+K_KINDS = 8
+KIND_NAMES = ["peel", "exec_decode", "exec_encode", "hybrid", "channel", "hybrid_warp", "hybrid_cta", "hybrid_apply"]
 
 
 class Profile(C.Structure):

@@ -38,15 +38,16 @@ struct HostCode {
 // << 11; padded to 8 bytes; u64 records[n_records], one per entry of level >= 2 in entry order: the entry's PRODUCED
 // members (members of its check that earlier entries produce) as 5 x 12-bit symbol indices (padding = the executor's
 // zero row), bit 63 = more than 5 (none listed); padded to 16 bytes.  n_records may be less than the number of such
-// entries (the executor then applies the rest in full-row form).  The peel kernel writes hdr, entries and lvl_off;
-// sched_records_kernel adds passes and records.
-inline int sched_blob_base_bytes(int m)      // without records
+// entries (the executor then applies the rest in full-row form).  The peel kernel writes hdr, entries and lvl_off
+// (n_records = n_passes = 0); the executor adds passes and records in shared memory (payload_exec.cuh).  The encoder's
+// static blob is complete (make_enc_blob).
+inline int sched_blob_max_bytes(int m)       // what the peel kernel writes per codeword: header, entries, level offsets
 {
-    return (16 + 4 * m + 2 * (m + 1) + 2 * m + 7) & ~7;
+    return (16 + 4 * m + 2 * (m + 1) + 15) & ~15;
 }
-inline int sched_blob_max_bytes(int m)       // with a record per entry
+inline int sched_area_bytes(int m, int records)   // a blob in the executor's shared memory: + passes + records
 {
-    return (sched_blob_base_bytes(m) + 8 * m + 15) & ~15;
+    return (sched_blob_max_bytes(m) + 2 * m + 8 * records + 15) & ~15;
 }
 constexpr int kSchedMaxRow = 4095;           // 12-bit symbol indices in the records
 inline int sched_zero_row(int n)             // the executor's all-zero row: behind its 256-row boxes, or (n > 3840) row 4095

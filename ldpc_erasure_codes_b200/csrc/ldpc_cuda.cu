@@ -26,7 +26,6 @@
 #include "payload_exec.cuh"
 #include "peel_schedule.cuh"
 #include "rs_gf256.cuh"
-#include "sched_records.cuh"
 
 using namespace ldpc;
 
@@ -155,7 +154,7 @@ static int cached_map(ldpc_ctx *c, CUtensorMap *out, const void *base, int rows,
 // context
 // ------------------------------------------------------------------------------------------
 struct ExecGeom {
-    int W = 0, nslot = 0, slot_bytes = 0, smem_bytes = 0, sched_area = 0;
+    int W = 0, nslot = 0, slot_bytes = 0, smem_bytes = 0, sched_area = 0, msk_words = 0;
 };
 
 struct ldpc_ctx {
@@ -208,7 +207,7 @@ struct ldpc_ctx {
     bool prof_on = false;
     struct ProfRec { cudaEvent_t a, b; int kind; };
     std::vector<ProfRec> prof_recs;
-    long long launches[LDPC_K_KINDS] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long launches[LDPC_K_KINDS] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 // brackets one kernel launch with events when profiling is on; always counts the launch
@@ -267,7 +266,8 @@ static int choose_geom(const ldpc_ctx *c, bool dynamic_sched, ExecGeom *g)
     const int n = c->code.n, S = c->S, m = c->code.m;
     const int nbox = (n + kBoxRows - 1) / kBoxRows;
     const int cidx_bytes = m * c->code.RW * 2;
-    const int mask_bytes = dynamic_sched ? kExecMaxGroups * ((c->NW + 3) & ~3) * 4 : 0;   // hybrid mode: one mask per slot
+    const int msk_words = ((nbox * kBoxRows + 8) / 32 + 1 + 3) & ~3;   // a codeword's mask + the (zero) bits of the zero rows
+    const int mask_bytes = dynamic_sched ? kExecMaxGroups * msk_words * 4 : 0;
     const int fixed = cidx_bytes + mask_bytes + 64 + 128 + 128;   // check rows, masks, barriers, mailboxes, base alignment
     // a blob in shared memory: the static schedule whole; a per-codeword schedule with at least 64 records and, if
     // there is room, one per check (the peel kernel emits what fits, entries past that take the full-row form)
@@ -277,9 +277,8 @@ static int choose_geom(const ldpc_ctx *c, bool dynamic_sched, ExecGeom *g)
         if (c->force_W && W != c->force_W) continue;
         const int slot = nbox * kBoxRows * W + kExecZeroRowBytes;
         if ((slot - kExecZeroRowBytes) / 16 > 0xFFFF) continue;   // check rows are staged as 16-bit offsets in 16-byte units
-        const int blob_min = dynamic_sched ? ((sched_blob_base_bytes(m) + 8 * std::min(m, 64) + 15) & ~15)
-                                           : int(make_enc_blob(c->code, 32 / (W / 16)).size());
-        const int blob_max = dynamic_sched ? sched_blob_max_bytes(m) : blob_min;
+        const int blob_min = dynamic_sched ? sched_area_bytes(m, std::min(m, 64)) : int(make_enc_blob(c->code, 32 / (W / 16)).size());
+        const int blob_max = dynamic_sched ? sched_area_bytes(m, m) : blob_min;
         int nslot;
         if (dynamic_sched) nslot = (c->smem_optin - fixed) / (slot + blob_min);
         else nslot = (c->smem_optin - fixed - blob_min) / slot;
@@ -289,7 +288,7 @@ static int choose_geom(const ldpc_ctx *c, bool dynamic_sched, ExecGeom *g)
         int blob = blob_min;
         if (dynamic_sched) blob = std::min(blob_max, ((c->smem_optin - fixed - nslot * slot) / nslot) & ~15);
         ExecGeom cand;
-        cand.W = W; cand.nslot = nslot; cand.slot_bytes = slot; cand.sched_area = blob;
+        cand.W = W; cand.nslot = nslot; cand.slot_bytes = slot; cand.sched_area = blob; cand.msk_words = msk_words;
         cand.smem_bytes = nslot * slot + (dynamic_sched ? nslot : 1) * blob + cidx_bytes + mask_bytes + 64 + 128;
         if (!best.W || (best.nslot < 3 && cand.nslot > best.nslot)) best = cand;
         if (best.nslot >= 3) break;
@@ -596,7 +595,7 @@ static int launch_exec(ldpc_ctx *c, const ExecGeom &g, const void *d_in, int row
     p.sched_max = g.sched_area; p.m = c->code.m; p.RW = c->code.RW; p.rows_in = rows_in; p.rows_out = rows_out;
     p.nbox_in = (rows_in + kBoxRows - 1) / kBoxRows; p.nbox_out = (rows_out + kBoxRows - 1) / kBoxRows;
     p.slices = c->S / g.W; p.nslot = g.nslot; p.slot_bytes = g.slot_bytes;
-    p.zrow = sched_zero_row(c->code.n); p.out = static_cast<uint8_t *>(d_out); p.S = c->S;
+    p.zrow = sched_zero_row(c->code.n); p.out = static_cast<uint8_t *>(d_out); p.S = c->S; p.n = c->code.n; p.msk_words = g.msk_words;
     p.phase_cycles = sched_stride ? c->d_phase : nullptr;
     int rwm = 0;
     ExecKernel k = pick_exec(g.W, c->code.max_row_weight, &rwm);
@@ -841,28 +840,6 @@ static int decode_chunk(ldpc_ctx *c, const uint8_t *d_cw, const uint32_t *d_mask
     { int rcd = debug_sync("peel_schedule_kernel", st); if (rcd) return rcd; }
     const bool pattern_only = d_cw == nullptr;   // error-rate run: no payload
     if (!pattern_only) {
-        // records of the produced members, for the executor's level walk
-        RecParams rp;
-        rp.mask = d_mask; rp.sched = sched; rp.sched_len = sched_len; rp.cidx = c->d_cidx; rp.B = B; rp.n = c->code.n; rp.m = c->code.m;
-        rp.RW = c->code.RW; rp.NW = c->NW; rp.stride = c->sched_stride; rp.blob_cap = c->dec.sched_area; rp.zrow = sched_zero_row(c->code.n); rp.epw = 32 / (c->dec.W / 16);
-        const int rsmem = c->code.m * c->code.RW * 2 + kRecWarps * ((c->NW + 1 + 3) & ~3) * 4;
-        const int rgrid = int(std::min<long long>((B + kRecWarps - 1) / kRecWarps, (long long)c->num_sms * 8));
-        typedef void (*RecKernel)(const RecParams);
-        RecKernel rk = nullptr;
-        switch (c->code.RW / 8) {
-            case 1: rk = sched_records_kernel<1>; break;
-            case 2: rk = sched_records_kernel<2>; break;
-            case 3: rk = sched_records_kernel<3>; break;
-            case 4: rk = sched_records_kernel<4>; break;
-            default: return fail(LDPC_ERR_UNSUPPORTED, "row weight above 32");
-        }
-        if (rsmem > 48 * 1024) { int rcs = allow_max_smem(reinterpret_cast<const void *>(rk), c->smem_optin); if (rcs) return rcs; }
-        {
-            ProfScope ps(c, LDPC_K_RECORDS, st);
-            rk<<<rgrid, kRecWarps * 32, rsmem, st>>>(rp);
-        }
-        CUDA_TRY(cudaGetLastError());
-        { int rcd = debug_sync("sched_records_kernel", st); if (rcd) return rcd; }
         int rc = launch_exec(c, c->dec, d_cw, c->code.n, d_out, c->code.k, sched, sched_len, c->sched_stride, B, st,
                              mode == LDPC_MODE_HYBRID ? c->hyb.d_synd : nullptr, d_mask);
         if (rc) return rc;

@@ -31,9 +31,11 @@
 //      Rounds run from the highest level down: an entry never reads the target of an entry of the same
 //      or a higher level, so a round's stores cannot disturb a later round's gathers.
 //   2. WALK: entry i of level >= 2 is  row[v_i] = s_i ^ XOR of its PRODUCED members (erased originally,
-//      recovered at a lower level: ~2.6 per entry at 20 %), which the schedule lists in an 8-byte record
-//      per entry (sched_records.cuh; hmat.cpp for the encoder): 6 loads and one store per pass of <= 32 / LPG
-//      entries of one level.  A warp issues in order and a pass is ~90 instructions with its bookkeeping
+//      recovered at a lower level: ~2.6 per entry at 20 %), listed in an 8-byte record per entry: 6 loads
+//      and one store per pass of <= 32 / LPG entries of one level.  The records and the list of passes depend on
+//      the erasure mask alone; the group builds them (one thread per entry tests the members of the entry's check
+//      against the mask) in the shadow of the slot's TMA load: the blob and the mask are small and land first, on
+//      their own barrier.  The encoder's static blob carries its records and passes ready made (hmat.cpp).  A warp issues in order and a pass is ~90 instructions with its bookkeeping
 //      (which entries, entry word, record, addresses), so the passes rotate over the group's four warps:
 //      the passes are listed in the blob; warp p % 4 prepares pass p while the three passes before it run, waits for pass p-1 on a named
 //      barrier (bar.sync / bar.arrive between two warps), then only loads, XORs, stores and signals.
@@ -72,8 +74,9 @@ struct ExecParams {
     int slot_bytes;             // shared bytes per slot (payload rows + the zero row)
     int zrow;                   // row index of the all-zero row inside a slot (sched_zero_row)
     uint8_t *synd;              // hybrid mode: [B][m][S] check syndromes of the codewords that still have erasures, or nullptr
-    const uint32_t *mask;       // hybrid mode: [B][NW] erasure masks (erased rows are zeroed in the slot before the XOR phase)
-    int NW;
+    const uint32_t *mask;       // per-codeword schedules: [B][NW] erasure masks
+    int NW, n;
+    int msk_words;              // mask words per slot: covers the bits of the zero rows behind the slot
     uint8_t *out;               // [B][rows_out][S]: the output the tensor maps describe (the walk's symbols are re-stored with plain stores)
     int S;
     int nfull_in, nfull_out;    // whole 256-row boxes moved by ONE 4-D tensor copy (map [B][rows/256][256][S]); the rest box by box
@@ -107,6 +110,7 @@ payload_exec_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
     constexpr int W_SH = LPG_SH + 4;                  // log2(W)
     constexpr int GT = kExecWarpsPerGroup * 32;       // threads per group
     constexpr int NGROUPS = GT / LPG;                 // entries a group handles per pass
+    constexpr int EPW = 32 / LPG;                     // entries per pass of the walk
     constexpr int R = kExecBulkRound;
     extern __shared__ __align__(128) uint8_t smem[];
     // layout: [slots][blobs: nslot (per-codeword schedules) or 1 (static)][check rows][masks (hybrid)][barriers][unit mailboxes]
@@ -115,9 +119,9 @@ payload_exec_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
     uint8_t *blobs = slots + size_t(p.nslot) * p.slot_bytes;
     uint16_t *cidx_s = reinterpret_cast<uint16_t *>(blobs + size_t(dynamic ? p.nslot : 1) * p.sched_max);
     uint32_t *masks = reinterpret_cast<uint32_t *>(cidx_s + size_t(p.m) * (RWQ * 8));
-    const int msk_words = p.synd ? ((p.NW + 3) & ~3) : 0;
-    uint64_t *full = reinterpret_cast<uint64_t *>(masks + size_t(p.nslot) * msk_words);   // [nslot]
-    int *mailbox = reinterpret_cast<int *>(full + 8);        // [g] unit of group g, [8] next unit
+    const int msk_words = dynamic ? p.msk_words : 0;
+    uint64_t *full = reinterpret_cast<uint64_t *>(masks + size_t(p.nslot) * msk_words);   // [nslot] the slot's payload; [4 + nslot] its blob
+    int *mailbox = reinterpret_cast<int *>(full + 8);        // [g] unit of group g, [8] next unit, [12 + g] blob bytes of group g's unit
 
     const int g = threadIdx.x / GT;          // group = slot
     const int tg = threadIdx.x % GT;         // thread in group
@@ -167,6 +171,7 @@ payload_exec_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
         const uint4 *src = reinterpret_cast<const uint4 *>(p.rows);
         uint4 *dst = reinterpret_cast<uint4 *>(cidx_s);
         for (int i = threadIdx.x; i < p.m * RWQ; i += blockDim.x) dst[i] = src[i];
+        for (int i = threadIdx.x; i < p.nslot * msk_words; i += blockDim.x) masks[i] = 0u;   // (the words behind the codeword's NW stay zero)
         if (!dynamic) {
             const uint4 *s2 = reinterpret_cast<const uint4 *>(p.sched);
             uint4 *d2 = reinterpret_cast<uint4 *>(blobs);
@@ -178,7 +183,7 @@ payload_exec_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
             if ((threadIdx.x % 8) * 16 < W) reinterpret_cast<uint4 *>(slots + off)[threadIdx.x % 8] = make_uint4(0u, 0u, 0u, 0u);
         }
         if (threadIdx.x == 0) {
-            for (int s = 0; s < p.nslot; s++) mbar_init(&full[s], 1);
+            for (int s = 0; s < p.nslot; s++) { mbar_init(&full[s], 1); mbar_init(&full[4 + s], 1); }
             mailbox[8] = 0;
             mbar_fence_init();
         }
@@ -230,11 +235,15 @@ payload_exec_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
                 const long long b = blockIdx.x + (long long)(j / p.slices) * gridDim.x;
                 const int sl = j % p.slices;
                 const uint32_t blen = blen_next;
-                mbar_arrive_expect_tx(&full[g], uint32_t(p.nbox_in) * kBoxRows * W + blen);
+                if (dynamic) {      // the blob first, on its own barrier: the group works on it while the slot loads
+                    mailbox[12 + g] = int(blen);
+                    mbar_arrive_expect_tx(&full[4 + g], blen);
+                    bulk_load_1d(blob, p.sched + b * (long long)p.sched_stride, blen, &full[4 + g]);
+                }
+                mbar_arrive_expect_tx(&full[g], uint32_t(p.nbox_in) * kBoxRows * W);
                 if (p.nfull_in) tma_load_4d(slot, &in4_map, sl * W, 0, 0, int(b), &full[g]);
                 for (int i = p.nfull_in; i < p.nbox_in; i++)
                     tma_load_3d(slot + size_t(i) * kBoxRows * W, &in_map, sl * W, i * kBoxRows, int(b), &full[g]);
-                if (dynamic) bulk_load_1d(blob, p.sched + b * (long long)p.sched_stride, blen, &full[g]);
                 claim();
             }
         }
@@ -242,27 +251,91 @@ payload_exec_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
         const int j = mailbox[g];
         if (j >= n_units) break;
         lap(0);
-        if (p.synd) {   // hybrid mode: fetch the codeword's erasure mask while the slot loads
+        const uint32_t *hdr = reinterpret_cast<const uint32_t *>(blob);
+        int ne, nl, nrec, npass, n1;
+        const uint32_t *ent;
+        const uint16_t *lvo;
+        uint32_t pt_a, rec_a;              // shared-space addresses of the pass table and the records
+        if (dynamic) {
+            // the codeword's erasure mask, then -- while the slot loads -- the passes and records of the walk
             const long long b = blockIdx.x + (long long)(j / p.slices) * gridDim.x;
-            for (int w = tg; w < p.NW; w += GT) msk_s[w] = p.mask[b * p.NW + w];
+            for (int w = tg; w < p.NW; w += GT) {
+                uint32_t x = p.mask[b * p.NW + w];
+                if (w == p.NW - 1 && (p.n & 31)) x &= 0xFFFFFFFFu >> (32 - (p.n & 31));
+                msk_s[w] = x;
+            }
+            mbar_wait(&full[4 + g], phase);
+            named_bar_sync(bar_id, GT);        // the mask words
+            ne = int(hdr[0]); nl = int(hdr[1] & 0xFFFFu);
+            ent = hdr + 4;
+            lvo = reinterpret_cast<const uint16_t *>(ent + ne);
+            n1 = nl >= 2 ? int(lvo[1]) : ne;   // entries of the first level: no produced members, no record
+            pt_a = smem_u32(lvo) + 2u * uint32_t(nl + 1);
+            // passes: level index L = 1 .. nl-1 covers entries [lvo[L], lvo[L+1]), cut into pieces of <= EPW
+            // (every warp computes the count; warp 0 writes the table: first entry | (count - 1) << 11)
+            npass = 0;
+            for (int L0 = 1; L0 < nl; L0 += 32) {
+                const int L = L0 + (tg & 31);
+                const int s0 = L < nl ? int(lvo[L]) : 0, s1 = L < nl ? int(lvo[L + 1]) : 0;
+                const int np = (s1 - s0 + EPW - 1) / EPW;
+                int inc = np;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+                    if ((tg & 31) >= o) inc += t;
+                }
+                if (wg == 0) {
+                    uint32_t at = pt_a + 2u * uint32_t(npass + inc - np);
+                    for (int pos = s0; pos < s1; pos += EPW, at += 2u) {
+                        const unsigned short pw = (unsigned short)(pos | ((min(EPW, s1 - pos) - 1) << 11));
+                        asm volatile("st.shared.u16 [%0], %1;" ::"r"(at), "h"(pw) : "memory");
+                    }
+                }
+                npass += __shfl_sync(0xFFFFFFFFu, inc, 31);
+            }
+            rec_a = (pt_a + 2u * uint32_t(npass) + 7u) & ~7u;
+            const int room = (int(smem_u32(blob)) + p.sched_max - int(rec_a)) / 8;
+            nrec = max(0, min(ne - n1, room));
+            // records: the members of the entry's check that were erased on arrival, the target excepted
+            const unsigned long long z = (unsigned long long)uint32_t(p.zrow);
+            for (int i = tg; i < nrec; i += GT) {
+                const uint32_t e = ent[n1 + i];
+                const uint32_t voff16 = (e & 0xFFFFu) * LPG;
+                uint32_t rr[RWQ * 4];
+                load_row(e >> 16, rr);
+                unsigned long long rec = 0ull;
+                int nd = 0;
+#pragma unroll
+                for (int t = 0; t < SL; t++) {
+                    const uint32_t o16 = (t & 1) ? (rr[t >> 1] >> 16) : (rr[t >> 1] & 0xFFFFu);
+                    const uint32_t u = o16 >> LPG_SH;
+                    const bool hit = ((msk_s[u >> 5] >> (u & 31)) & 1u) && o16 != voff16;
+                    if (hit) { rec = (rec << 12) | u; nd++; }
+                }
+#pragma unroll
+                for (int q = 0; q < 5; q++)
+                    if (q >= nd) rec = (rec << 12) | z;
+                if (nd > 5) rec = z | (z << 12) | (z << 24) | (z << 36) | (z << 48) | (1ull << 63);
+                asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(rec_a + 8u * uint32_t(i)), "r"(uint32_t(rec)), "r"(uint32_t(rec >> 32)) : "memory");
+            }
+        } else {
+            ne = int(hdr[0]); nl = int(hdr[1] & 0xFFFFu); nrec = int(hdr[1] >> 16); npass = int(hdr[2] >> 16);
+            ent = hdr + 4;
+            lvo = reinterpret_cast<const uint16_t *>(ent + ne);
+            n1 = nl >= 2 ? int(lvo[1]) : ne;
+            pt_a = smem_u32(lvo) + 2u * uint32_t(nl + 1);
+            rec_a = (pt_a + 2u * uint32_t(npass) + 7u) & ~7u;
         }
         mbar_wait(&full[g], phase);
         phase ^= 1u;
         lap(1);
 
-        const uint32_t *hdr = reinterpret_cast<const uint32_t *>(blob);
-        const int ne = int(hdr[0]);
-        const int nl = int(hdr[1] & 0xFFFFu), nrec = int(hdr[1] >> 16);
-        const uint32_t *ent = hdr + 4;
-        const uint16_t *lvo = reinterpret_cast<const uint16_t *>(ent + ne);
-        const int n1 = nl >= 2 ? int(lvo[1]) : ne;     // entries of the first level: no produced members, no record
         const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
         const bool resid = p.synd && (hdr[2] & 0xFFFFu) != 0u;     // (uniform over the group)
         if (resid) {
             // Hybrid mode, the codeword keeps erasures after peeling: symbols that stay unknown must read as
             // zero when the syndromes are formed below, so every erased row is zeroed (a superset of the rows
             // the schedule produces).
-            named_bar_sync(bar_id, GT);   // the mask words
             for (int u = eslot; u < p.rows_in; u += NGROUPS)
                 if ((msk_s[u >> 5] >> (u & 31)) & 1u) sts128(base_a + u * W, z4);
         } else {
@@ -319,13 +392,10 @@ payload_exec_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
         }
 
         // ---- 2. walk the levels >= 2: pass p (<= EPW entries of one level, listed in the blob) belongs to warp p % 4 ----
-        const int npass = int(hdr[2] >> 16);
         if (npass > 0) {
             const uint32_t z = uint32_t(p.zrow);
             const uint32_t zlo = z | (z << 12) | (z << 24), zhi = (z >> 8) | (z << 4) | (z << 16);
             const uint32_t ent_a = smem_u32(ent);
-            const uint32_t pt_a = smem_u32(lvo) + 2u * uint32_t(nl + 1);
-            const uint32_t rec_a = (pt_a + 2u * uint32_t(npass) + 7u) & ~7u;
             const int hand_in = 4 + g * 4 + ((wg + 3) & 3), hand_out = 4 + g * 4 + wg;
             uint32_t f_e, f_lo, f_hi;
             auto fetch = [&](int pass) {       // entry word and record of my lane's entry in that pass

@@ -29,7 +29,7 @@ def test_header_symbols_are_all_exported(lib):
 
 
 def test_abi_version(lib):
-    assert lib.ldpc_cuda_abi_version() == 3
+    assert lib.ldpc_cuda_abi_version() == 2
 
 
 def test_argument_errors_do_not_need_a_gpu(lib):
