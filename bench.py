@@ -15,13 +15,19 @@ before the timed region.
   value     = N_gpus * codewords_per_step * k * S * 8 / step time  (info bits, main.cpp:655)
   e2e       = same metric through ldpc_decode_host(): pinned HOST buffers, H2D + kernels + D2H
               inside the timed region (a smaller batch per step, stated in the JSON)
-  roofline  = payload_exec_kernel (the dominant kernel): algorithmic bytes per launch /
-              CUDA-event time of that kernel, against MEASURED_PEAKS.json hbm_gbs
-  cpu_baseline = the reference algorithm restated in C (oracle/, OpenMP over codewords) on this
-              box's host cores, bounded sample
+  roofline  = the WHOLE decode (peel_schedule_kernel + payload_exec_kernel of every chunk): algorithmic
+              bytes of the step / device time of the step, against MEASURED_PEAKS.json hbm_gbs;
+              roofline.exec_kernel = the same for payload_exec_kernel alone (the kernel that moves
+              the bytes), from CUDA events around each of its launches
+  config.hybrid / config.encode / config.goodput_gbps = the same workload through mode=hybrid,
+              through ldpc_encode, and the information of the frames that decoded (fail == 0)
+  cpu_baseline = the reference algorithm restated in C (oracle/ldpc_oracle.c, early stop, OpenMP
+              over codewords) on this box's host cores, bounded sample
 
-`--impl reference` times that CPU restatement alone (PoCL / the Intel FPGA OpenCL SDK / MATLAB
-are not installable offline, so the reference's own implementation cannot run here).
+`--impl reference` times the REFERENCE'S OWN decoder source (OpenCL/device/ldpc_erasure_decoder.cl,
+compiled unmodified by gcc behind oracle/ref_shim: oracle/_ref/libldpc_ref.so, one host thread per
+core) on the same workload; where that library is missing, or for modes it has no source for
+(hybrid: MATLAB only), the C restatement.
 """
 from __future__ import annotations
 
@@ -54,7 +60,10 @@ def parse_args():
     ap.add_argument("-i", "--max-iter", type=int, default=50, help="sweeps over the checks (reference flag -i, default 50)")
     ap.add_argument("-c", "--code", type=int, default=1, help="0 = (2000,1000), 1 = (2040,1530) [the benchmark], 2 = (4000,2000)")
     ap.add_argument("--mode", default="peel", choices=["peel", "hybrid"])
-    ap.add_argument("--e2e-batch", type=int, default=1 << 15)
+    ap.add_argument("--model", default="iid", choices=["iid", "bursty"], help="erasure channel: i.i.d. at -p/64, or the two-state bursty model")
+    ap.add_argument("--bursty", default="0.1,0.4,10", help="alpha,beta,bias of the bursty model (Bursty_Error_Channel_Model_Generator.m)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the hybrid / encode sub-records")
+    ap.add_argument("--e2e-batch", type=int, default=1 << 16)
     ap.add_argument("--seed", type=int, default=12345)
     ap.add_argument("--slice-bytes", type=int, default=0)
     ap.add_argument("--slots", type=int, default=0)
@@ -69,14 +78,40 @@ def algorithmic_bytes_decode(n, k, S):
     return n * S + (n + 7) // 8 + k * S + 1
 
 
+def workload_name(args):
+    """The same string in both arms (the driver compares them); sizes live in their own config keys."""
+    chan = (f"{args.per64}/64 ({100 * args.per64 / 64:.1f}%) i.i.d. erasures" if args.model == "iid"
+            else f"bursty two-state erasures (alpha,beta,bias = {args.bursty})")
+    return f"{CODE_NAMES[CODE_IND]}, {args.symbol_bytes}-byte symbols, {chan}, {args.mode} decode, max_iter {args.max_iter}"
+
+
+def bursty_params(args):
+    a, b, c = (float(x) for x in args.bursty.split(","))
+    return (a, b, c)
+
+
 # ------------------------------------------------------------------------------------------
-# CPU reference arm (the oracle = restatement of ldpc_erasure_decoder.cl, all host cores)
+# CPU reference arm: the reference's own decoder source (oracle/_ref) or the C restatement (oracle/ldpc_oracle.c)
 # ------------------------------------------------------------------------------------------
-def cpu_decode_rate(S, P, seed, seconds, max_iter, mode="peel"):
-    """Returns (info Gbit/s, threads, sample description, codewords, elapsed)."""
+def ref_usable(args):
+    """oracle/_ref holds the reference's peeling decoder for its two OpenCL codes at 16/64/1024-byte symbols."""
+    if args.mode != "peel" or CODE_IND not in (0, 1) or args.symbol_bytes not in (16, 64, 1024):
+        return False
+    try:
+        from oracle import ref
+        return ref.available()
+    except Exception:
+        return False
+
+
+def cpu_decode_rate(args, seed, seconds, kind):
+    """One bounded sample of the workload on the host cores.  kind = "reference": ldpc_erasure_decoder.cl itself (no early
+    stop: max_iter full sweeps, as committed); "port": the restatement with the early stop of ldpc_erasure_decoder_old.pro.
+    Returns (info Gbit/s, threads, sample description, codewords, elapsed)."""
     import numpy as np
     from oracle import oracle as orc
 
+    S, P = args.symbol_bytes, args.per64
     code = orc.Code.builtin(CODE_IND)
     # all host threads this process may use (torchrun exports OMP_NUM_THREADS=1: ask explicitly)
     threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
@@ -85,37 +120,50 @@ def cpu_decode_rate(S, P, seed, seconds, max_iter, mode="peel"):
     def make(B, frame0):
         info = rng.integers(0, 256, (B, code.k, S), dtype=np.uint8)
         cw = orc.encode(code, info)
-        flags = orc.gen_erasures_iid(code.n, seed, B, P=P, frame0=frame0)
+        if args.model == "iid":
+            flags = orc.gen_erasures_iid(code.n, seed, B, P=P, frame0=frame0)
+        else:
+            flags, _ = orc.gen_erasures_bursty(code.n, seed, B, *bursty_params(args), frame0=frame0)
         cw[flags == 1] = 0
         return cw, flags
 
+    if kind == "reference":
+        from oracle import ref
+
+        def run(cw, flags):
+            ref.decode(CODE_IND, cw, flags, num_iter=args.max_iter, variant="canon", nthreads=threads)
+        what = "OpenCL/device/ldpc_erasure_decoder.cl compiled by gcc (oracle/_ref), no early stop"
+    else:
+        def run(cw, flags):
+            orc.decode(code, cw, flags, max_iter=args.max_iter, mode=args.mode, inplace=True, nthreads=threads)
+        what = "C restatement (oracle/ldpc_oracle.c), early stop"
+
     # calibrate on a small batch, then size the sample for ~`seconds` of CPU work
-    cw, flags = make(64 * threads, 0)
+    cw, flags = make(16 * threads, 0)
     t0 = time.perf_counter()
-    orc.decode(code, cw, flags, max_iter=max_iter, mode=mode, inplace=True, nthreads=threads)
+    run(cw, flags)
     dt = time.perf_counter() - t0
-    rate = 64 * threads / dt
-    B = int(max(64 * threads, min(rate * seconds, 262144)))
+    rate = 16 * threads / dt
+    B = int(max(16 * threads, min(rate * seconds, 262144)))
     cw, flags = make(B, 1 << 20)
     t0 = time.perf_counter()
-    orc.decode(code, cw, flags, max_iter=max_iter, mode=mode, inplace=True, nthreads=threads)
+    run(cw, flags)
     dt = time.perf_counter() - t0
     gbps = B * code.k * S * 8 / dt / 1e9
-    return gbps, threads, f"{B} codewords {CODE_NAMES[CODE_IND].split()[0]} S={S} P={P}/64, reference sweep decoder, early stop", B, dt
+    return gbps, threads, f"{B} codewords of the workload, {what}, {threads} host threads", B, dt
 
 
 def run_reference(args):
-    """--impl reference: K timed steps of the CPU restatement, each a bounded sample."""
+    """--impl reference: K timed steps on the host cores, each a bounded sample of the workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    kind = "reference" if ref_usable(args) else "port"
     per_step = max(1.0, min(args.cpu_seconds, 60.0 / max(1, args.steps + args.warmup)))
-    vals = []
-    threads, sample = 1, ""
-    ms = []
+    vals, ms = [], []
+    threads, sample, B = 1, "", 0
     for i in range(args.warmup + args.steps):
-        g, threads, sample, B, dt = cpu_decode_rate(args.symbol_bytes, args.per64, args.seed + i, per_step,
-                                                    args.max_iter, args.mode)
+        g, threads, sample, B, dt = cpu_decode_rate(args, args.seed + i, per_step, kind)
         if i >= args.warmup:
             vals.append(g)
             ms.append(dt * 1e3)
@@ -124,15 +172,18 @@ def run_reference(args):
         "impl": "reference", "metric": "decoded info Gbit/s (n2040 k1530, 20% erasures)", "value": v, "unit": "Gbit/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sum(ms) / len(ms),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": f"{CODE_NAMES[CODE_IND]}, {args.symbol_bytes}-byte symbols, {args.per64}/64 "
-                               f"({100 * args.per64 / 64:.1f}%) i.i.d. erasures, {args.mode} decode",
-                   "symbol_bytes": args.symbol_bytes, "per64": args.per64, "max_iter": args.max_iter, "mode": args.mode},
-        "cpu_baseline": {"value": v, "unit": "Gbit/s", "cores": threads, "kind": "port", "sample": sample},
+        "config": {"workload": workload_name(args), "symbol_bytes": args.symbol_bytes, "per64": args.per64,
+                   "max_iter": args.max_iter, "mode": args.mode, "codewords_per_step": B},
+        "cpu_baseline": {"value": v, "unit": "Gbit/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": "Gbit/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-        "note": "reference algorithm restated in C (oracle/ldpc_oracle.c) on host cores; the reference's own "
-                "Intel-FPGA OpenCL / MATLAB code cannot run here (no PoCL, no aoc, no MATLAB offline)",
+        "note": ("the reference's own decoder source, unmodified, behind a C shim (channels as arrays), one pthread per core"
+                 if kind == "reference" else
+                 "reference algorithm restated in C (oracle/ldpc_oracle.c): oracle/_ref has no source for this mode / code / symbol size"),
     }
+    if kind == "reference":   # beside it: the restatement with the early stop of ldpc_erasure_decoder_old.pro
+        g2, _, s2, _, _ = cpu_decode_rate(args, args.seed, min(per_step, 5.0), "port")
+        line["port_with_early_stop"] = {"value": g2, "unit": "Gbit/s", "sample": s2}
     print(json.dumps(line), flush=True)
 
 
@@ -230,7 +281,10 @@ def run_b200(args):
     for r in range(resident):
         fill_random(info, seed=args.seed, block0=(frame_base + r * sub) * k * S // 16)
         codec.encode(info, out=rx[r])
-        codec.gen_erasures(sub, args.seed, P=P, frame0=frame_base + r * sub, payload=rx[r], mask=masks[r])
+        if args.model == "iid":
+            codec.gen_erasures(sub, args.seed, P=P, frame0=frame_base + r * sub, payload=rx[r], mask=masks[r])
+        else:
+            codec.gen_erasures(sub, args.seed, bursty=bursty_params(args), frame0=frame_base + r * sub, payload=rx[r], mask=masks[r])
     torch.cuda.synchronize()
 
     rx_all, masks_all = rx.view(resident * sub, n, S), masks.view(resident * sub, codec.mask_words)
@@ -300,20 +354,67 @@ def run_b200(args):
     except Exception:
         pass
 
+    def timed(fn, reps):
+        """device time of fn() per call, CUDA events on the launching stream, after one untimed call"""
+        fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return sharding.reduce_max(a.elapsed_time(b)) / reps
+
+    # ---- the same workload through mode = hybrid (10 sweeps + GF(2) elimination on the residual sets) and
+    # ---- through the encoder (config 5: "encode+decode"); informational sub-records of the line
+    hybrid_rec = encode_rec = None
+    if not args.no_extras:
+        if args.mode == "peel":
+            fail_h = torch.empty_like(fail_all)
+            codec.reset_stats()
+
+            def hyb():
+                for i in range(0, n_sub, resident):
+                    cnt = min(resident, n_sub - i) * sub
+                    codec.decode(rx_all[:cnt], masks_all[:cnt], max_iter=10, mode="hybrid", out=out_all[:cnt], fail=fail_h[:cnt])
+            ms_h = timed(hyb, 2)
+            st_h = codec.stats()
+            fer_h = float(fail_h.float().mean().item())
+            val_h = world * codewords * k * S * 8 / (ms_h * 1e-3) / 1e9
+            hybrid_rec = {"value": val_h, "unit": "Gbit/s", "ms_per_step": ms_h, "max_iter": 10, "frame_error_rate": fer_h,
+                          "goodput_gbps": val_h * (1.0 - fer_h),
+                          "whole_step_frac": (algorithmic_bytes_decode(n, k, S) * codewords / (ms_h * 1e-3) / 1e9) / peak,
+                          "frames_through_elimination": st_h["ml_attempts"] / max(1, st_h["frames"]),
+                          "rank_deficient_frames": st_h["ml_failures"]}
+            step()      # (the peel outputs back in place for the checks below)
+        cw_enc = rx[0]      # encode the first sub-batch's information again, over its received words (restored below)
+        fill_random(info, seed=args.seed, block0=(frame_base + 0 * sub) * k * S // 16)
+        ms_e = timed(lambda: codec.encode(info, out=cw_enc), 3)
+        if args.model == "iid":
+            codec.gen_erasures(sub, args.seed, P=P, frame0=frame_base, payload=rx[0], mask=masks[0])
+        else:
+            codec.gen_erasures(sub, args.seed, bursty=bursty_params(args), frame0=frame_base, payload=rx[0], mask=masks[0])
+        torch.cuda.synchronize()
+        enc_bytes = (k * S + n * S) * sub
+        encode_rec = {"value": world * sub * k * S * 8 / (ms_e * 1e-3) / 1e9, "unit": "Gbit/s", "ms_per_launch": ms_e, "codewords": sub,
+                      "achieved_gbs": enc_bytes / (ms_e * 1e-3) / 1e9, "frac": enc_bytes / (ms_e * 1e-3) / 1e9 / peak,
+                      "algorithmic_bytes_per_codeword": (k + n) * S}
+
     # ---- end to end through the host-buffer entry point -------------------------------------
     e2e = None
     if not args.no_e2e:
-        eb = min(args.e2e_batch, sub)
+        eb = min(args.e2e_batch, resident * sub)
         h_cw = torch.empty((eb, n, S), dtype=torch.uint8, pin_memory=True)
         h_mask = torch.empty((eb, codec.mask_words), dtype=torch.int32, pin_memory=True)
         h_out = torch.empty((eb, k, S), dtype=torch.uint8, pin_memory=True)
         h_fail = torch.empty((eb,), dtype=torch.uint8, pin_memory=True)
-        h_cw.copy_(rx[0][:eb])
-        h_mask.copy_(masks[0][:eb])
+        h_cw.copy_(rx_all[:eb])
+        h_mask.copy_(masks_all[:eb])
         torch.cuda.synchronize()
         for _ in range(2):
             codec.decode_host(h_cw, h_mask, max_iter=args.max_iter, mode=args.mode, out=h_out, fail=h_fail)
-        assert bool((h_out == out[0][:eb].cpu()).all()) and bool((h_fail == fail[0][:eb].cpu()).all())
+        assert bool((h_out == out_all[:eb].cpu()).all()) and bool((h_fail == fail_all[:eb].cpu()).all())
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
@@ -327,31 +428,34 @@ def run_b200(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        g, threads, sample, _, _ = cpu_decode_rate(S, P, args.seed, args.cpu_seconds, args.max_iter, args.mode)
+        g, threads, sample, _, _ = cpu_decode_rate(args, args.seed, args.cpu_seconds, "port")
         cpu = {"value": g, "unit": "Gbit/s", "cores": threads, "kind": "port", "sample": sample}
 
     if rank == 0:
+        whole_gbs = algorithmic_bytes_decode(n, k, S) * codewords / (ms_step * 1e-3) / 1e9
         line = {
             "metric": "decoded info Gbit/s (n2040 k1530, 20% erasures)", "value": value, "unit": "Gbit/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {
-                "workload": f"{CODE_NAMES[CODE_IND]}, {S}-byte symbols, {P}/64 ({100 * P / 64:.1f}%) i.i.d. erasures, "
-                            f"{codewords} codewords per GPU per step, {args.mode} decode",
-                "symbol_bytes": S, "per64": P, "max_iter": args.max_iter, "mode": args.mode,
+                "workload": workload_name(args),
+                "symbol_bytes": S, "per64": P, "max_iter": args.max_iter, "mode": args.mode, "model": args.model,
                 "codewords_per_gpu_per_step": codewords, "sub_batch": sub, "resident_sub_batches": resident,
                 "calls": "one ldpc_decode call per pass over the resident sub-batches; the library runs it as max_batch-sized chunks "
                          "(one peel + one executor launch each) alternating between two internal streams",
                 "l2": "every launch reads a distinct 8.5 GB sub-batch (>> 126 MB L2), no flush needed",
                 "slice_bytes": codec.info.slice_bytes, "exec_slots": codec.info.exec_slots,
-                "frame_error_rate": fer, "parallelism": f"codeword-sharded x{world}, no collectives",
-                "counters": job_stats,
+                "frame_error_rate": fer, "goodput_gbps": value * (1.0 - fer),
+                "parallelism": f"codeword-sharded x{world}, no collectives",
+                "counters": job_stats, "hybrid": hybrid_rec, "encode": encode_rec,
             },
-            "roofline": {"bound": "hbm", "kernel": "payload_exec_kernel(decode)", "achieved": achieved, "peak": peak,
-                         "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": exec_ms,
-                         "peel_schedule_ms_per_launch": peel_ms,
-                         "whole_step_frac": (algorithmic_bytes_decode(n, k, S) * codewords / (ms_step * 1e-3) / 1e9) / peak},
+            "roofline": {"bound": "hbm", "kernel": "whole ldpc_decode: peel_schedule_kernel + payload_exec_kernel per chunk",
+                         "achieved": whole_gbs, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": whole_gbs / peak,
+                         "traffic": traffic, "traffic_source": "ncu dram bytes of one smaller payload_exec launch, scaled per codeword (profiles/traffic.json); the peel kernel moves 0.3 KB per codeword",
+                         "algorithmic_bytes_per_step": algorithmic_bytes_decode(n, k, S) * codewords,
+                         "exec_kernel": {"kernel": "payload_exec_kernel(decode)", "achieved": achieved, "frac": achieved / peak,
+                                         "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": exec_ms},
+                         "peel_schedule_ms_per_launch": peel_ms},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
         print(json.dumps(line), flush=True)

@@ -437,7 +437,7 @@ extern "C" int ldpc_ctx_create(ldpc_ctx **out, const char *h_mat_path, int code_
     c->NW = (c->code.n + 31) / 32; c->MW = (c->code.m + 31) / 32;
     c->sched_stride = sched_blob_max_bytes(c->code.m);
     // hybrid mode keeps one syndrome set (m * S bytes) per codeword of a chunk: chunks are capped so that it stays <= 4 GiB
-    c->hybrid_batch = std::max<long long>(256, std::min<long long>(max_batch, (4ll << 30) / (size_t(c->code.m) * symbol_bytes)));
+    c->hybrid_batch = std::min<long long>(max_batch, std::max<long long>(256, (4ll << 30) / (size_t(c->code.m) * symbol_bytes)));   // (never above max_batch: the schedule scratch is sized for it)
 
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) { delete c; return fail(LDPC_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e)); }

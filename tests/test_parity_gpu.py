@@ -388,6 +388,16 @@ def test_hybrid_decode_bit_exact(codecs, P):
         assert (ref["status"] == 1).sum() > 20      # the elimination stage really ran and succeeded
 
 
+def test_hybrid_batch_larger_than_small_max_batch():
+    """A context created with max_batch < 256: hybrid chunks must not exceed it (the schedule scratch is sized for
+    max_batch codewords -- a round-2 regression found by tools/sanitize_pass.py: illegal address)."""
+    from ldpc_erasure_codes_b200.codec import LdpcCodec
+    codec = LdpcCodec(code=1, symbol_bytes=64, device=0, max_batch=16)
+    code, cw, rx, mask, flags = _scenario(codec, 1, 40, 13, 77, 64)
+    _hybrid_check(codec, code, rx, mask, flags)
+    codec.close()
+
+
 def test_hybrid_survey_frames(codecs):
     """(2040,1530), P=13/64, seed 12345: frame 0 (447 erasures) and frame 2 need elimination."""
     codec = codecs(1, 16)
