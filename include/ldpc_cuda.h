@@ -283,6 +283,26 @@ int rs_encode(rs_ctx *ctx, const void *d_info, void *d_cw, int64_t B, void *stre
 int rs_decode(rs_ctx *ctx, const void *d_cw, const uint32_t *d_mask, void *d_out,
               uint8_t *d_fail, int64_t B, void *stream);
 
+/* ---- code design (host only): girth-8 triangular-form H generator and short-cycle checker -----
+ * Replaces Matlab/Hgen_irregularDegree_no6cycles_systematic_encoding.m:94-224 ("bit filling": rows
+ * are filled with variables drawn with probability ~ (edges still needed)^3, a draw is kept iff it
+ * closes no 4- or 6-cycle; row r ends with the diagonal edge (r, k + r)) and
+ * Matlab/Cycle_Finder_length4_fromroot.m / Cycle_Finder_length6.m.  The draws come from a seeded
+ * generator (MATLAB's rand stream is not reproducible): same seed, same matrix.
+ * deg_c_prof / deg_v_prof: n_*_deg rows of (count, degree), degrees in DESCENDING order; the sums of
+ * count * degree must agree.  Output: dims = {m, n, nnz, 1}; CSR with ascending columns when
+ * row_ptr [m+1] / col_idx [col_cap >= nnz] are given (call once with NULLs to size them: nnz <=
+ * sum(count * degree) + m).  LDPC_ERR_UNSUPPORTED if no matrix was found in max_tries attempts.  */
+int ldpc_h_generate(const int32_t *deg_c_prof, int n_c_deg, const int32_t *deg_v_prof, int n_v_deg,
+                    uint64_t seed, int max_tries, int32_t dims[4], int32_t *row_ptr, int32_t *col_idx,
+                    int64_t col_cap, int32_t *tries_used);
+/* Number of variable nodes for which the reference's rooted finders report a cycle: length 4
+ * (Cycle_Finder_length4_fromroot.m) and length <= 6 (Cycle_Finder_length6.m, which counts a 4-cycle
+ * too).  Both zero <=> girth >= 8.                                                              */
+int ldpc_h_count_short_cycles(const int32_t *row_ptr, const int32_t *col_idx, int m, int n,
+                              int64_t *vars_on_4cycles, int64_t *vars_on_6cycles);
+const char *ldpc_h_last_error_string(void);
+
 /* ---- errors ------------------------------------------------------------------------- */
 const char *ldpc_last_error_string(void);
 int ldpc_cuda_abi_version(void);

@@ -14,7 +14,7 @@ SO = os.path.join(HERE, "libldpc_cuda.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 HOST_CXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
 
-SOURCES = ["ldpc_cuda.cu", "hmat.cpp"]
+SOURCES = ["ldpc_cuda.cu", "hmat.cpp", "hgen.cpp"]
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function", "-shared", "-ccbin", HOST_CXX,
