@@ -283,6 +283,28 @@ int rs_encode(rs_ctx *ctx, const void *d_info, void *d_cw, int64_t B, void *stre
 int rs_decode(rs_ctx *ctx, const void *d_cw, const uint32_t *d_mask, void *d_out,
               uint8_t *d_fail, int64_t B, void *stream);
 
+/* ---- non-binary GF(2^8) LDPC code -------------------------------------
+ * Matlab/ErasureCodes_NonBinaryLDPCSim.m, Matlab/My_LDPC_HybridML_NonBinary_Erasure_Decoder.m:
+ * the binary H of `base` keeps its structure, every edge carries a nonzero element of GF(2^8)
+ * (field polynomial 0x171); a check reads sum_u h[c][u] * y[u] = 0, the coefficient multiplying
+ * every byte of the S-byte symbol.  coef_csr: one coefficient per nonzero of H in row-major (CSR)
+ * order, or NULL to draw them as the simulation does (floor(255 * rand) + 1, sim :55) from
+ * Threefry4x32-20 with key {3, coef_seed}, counter = index of the nonzero.  The context borrows
+ * `base` (its peel kernel and scratch: the peeling schedule does not depend on the coefficients);
+ * `base` must outlive it and the two must not be used from two threads at once.
+ * encode: sim :176-182 (parity = inv(h_diag) * sum of h * c over the other members).
+ * decode: mode PEEL = the serial sweeps of decoder :19-55 (max_iter of them; reference: 10);
+ * mode HYBRID = then Gauss-Jordan over GF(2^8) on the residual set (:57-125); a column without
+ * pivot leaves the state after the sweeps and counts as ml_failure, as for the binary code.
+ * Buffers, masks, failure flags and counters as for ldpc_encode / ldpc_decode.                  */
+typedef struct ldpc_nb_ctx ldpc_nb_ctx;
+int ldpc_nb_ctx_create(ldpc_nb_ctx **out, ldpc_ctx *base, const uint8_t *coef_csr, uint32_t coef_seed);
+int ldpc_nb_ctx_destroy(ldpc_nb_ctx *ctx);
+int ldpc_nb_get_coefficients(const ldpc_nb_ctx *ctx, uint8_t *coef_csr);
+int ldpc_nb_encode(ldpc_nb_ctx *ctx, const void *d_info, void *d_cw, int64_t B, void *stream);
+int ldpc_nb_decode(ldpc_nb_ctx *ctx, const void *d_cw, const uint32_t *d_mask, void *d_out, uint8_t *d_fail,
+                   int max_iter, int mode, int64_t B, void *stream);
+
 /* ---- code design (host only): girth-8 triangular-form H generator and short-cycle checker -----
  * Replaces Matlab/Hgen_irregularDegree_no6cycles_systematic_encoding.m:94-224 ("bit filling": rows
  * are filled with variables drawn with probability ~ (edges still needed)^3, a draw is kept iff it

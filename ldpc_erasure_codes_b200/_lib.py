@@ -14,6 +14,7 @@ EXPORTS = [
     "ldpc_encode", "ldpc_gen_erasures", "ldpc_decode", "ldpc_decode_ex", "ldpc_simulate_fer", "ldpc_get_stats", "ldpc_reset_stats",
     "ldpc_encode_host", "ldpc_decode_host", "ldpc_decode_host_ex", "ldpc_encode_host_multi", "ldpc_decode_host_multi", "ldpc_fill_random", "ldpc_packetize", "ldpc_depacketize", "ldpc_ready_to_decode", "ldpc_profile_enable", "ldpc_profile_read",
     "rs_ctx_create", "rs_ctx_destroy", "rs_ctx_get_generator", "rs_encode", "rs_decode",
+    "ldpc_nb_ctx_create", "ldpc_nb_ctx_destroy", "ldpc_nb_get_coefficients", "ldpc_nb_encode", "ldpc_nb_decode",
     "ldpc_h_generate", "ldpc_h_count_short_cycles", "ldpc_h_last_error_string",
     "ldpc_last_error_string", "ldpc_cuda_abi_version",
 ]
@@ -90,6 +91,11 @@ def load():
     lib.rs_ctx_get_generator.argtypes = [vp, vp]
     lib.rs_encode.argtypes = [vp, vp, vp, i64, vp]
     lib.rs_decode.argtypes = [vp, vp, vp, vp, vp, i64, vp]
+    lib.ldpc_nb_ctx_create.argtypes = [C.POINTER(vp), vp, vp, u32]
+    lib.ldpc_nb_ctx_destroy.argtypes = [vp]
+    lib.ldpc_nb_get_coefficients.argtypes = [vp, vp]
+    lib.ldpc_nb_encode.argtypes = [vp, vp, vp, i64, vp]
+    lib.ldpc_nb_decode.argtypes = [vp, vp, vp, vp, vp, i32, i32, i64, vp]
     lib.ldpc_h_generate.argtypes = [vp, i32, vp, i32, u64, i32, C.POINTER(C.c_int32 * 4), vp, vp, i64, vp]
     lib.ldpc_h_count_short_cycles.argtypes = [vp, vp, i32, i32, C.POINTER(i64), C.POINTER(i64)]
     lib.ldpc_h_last_error_string.restype = C.c_char_p

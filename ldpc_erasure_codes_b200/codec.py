@@ -259,6 +259,64 @@ def pack_mask(flags):
     return np.packbits(pad, axis=1, bitorder="little").view(np.uint32).astype(np.int32, copy=False).reshape(B, nw)
 
 
+class NbLdpcCodec:
+    """Non-binary GF(256) LDPC code over the structure of a binary LdpcCodec (ldpc_nb_ctx; SURVEY 8(f) rank 3:
+    Matlab/ErasureCodes_NonBinaryLDPCSim.m, My_LDPC_HybridML_NonBinary_Erasure_Decoder.m).  coef = one nonzero field
+    element per nonzero of H in CSR order (numpy u8), or None to draw them from `seed` as the simulation does."""
+
+    def __init__(self, base: LdpcCodec, coef=None, seed=1):
+        import numpy as np
+        self.lib = _lib.load()
+        self.base = base
+        h = C.c_void_p()
+        cptr = None
+        if coef is not None:
+            coef = np.ascontiguousarray(coef, dtype=np.uint8)
+            assert coef.size == base.info.nnz
+            cptr = coef.ctypes.data_as(C.c_void_p)
+        _lib.check(self.lib.ldpc_nb_ctx_create(C.byref(h), base._h, cptr, seed & 0xFFFFFFFF))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.ldpc_nb_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def coefficients(self):
+        import numpy as np
+        out = np.zeros(self.base.info.nnz, dtype=np.uint8)
+        _lib.check(self.lib.ldpc_nb_get_coefficients(self._h, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def encode(self, info: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        b = self.base
+        B = info.shape[0]
+        assert info.dtype == torch.uint8 and info.is_contiguous() and tuple(info.shape[1:]) == (b.k, b.S)
+        if out is None:
+            out = torch.empty((B, b.n, b.S), dtype=torch.uint8, device=b.device)
+        _lib.check(self.lib.ldpc_nb_encode(self._h, _ptr(info), _ptr(out), B, _stream()))
+        return out
+
+    def decode(self, cw: torch.Tensor, mask: torch.Tensor, max_iter=10, mode="hybrid", out=None, fail=None):
+        b = self.base
+        B = cw.shape[0]
+        assert cw.dtype == torch.uint8 and cw.is_contiguous() and tuple(cw.shape[1:]) == (b.n, b.S)
+        assert mask.is_contiguous() and tuple(mask.shape) == (B, b.mask_words)
+        if out is None:
+            out = torch.empty((B, b.k, b.S), dtype=torch.uint8, device=b.device)
+        if fail is None:
+            fail = torch.empty((B,), dtype=torch.uint8, device=b.device)
+        _lib.check(self.lib.ldpc_nb_decode(self._h, _ptr(cw), _ptr(mask), _ptr(out), _ptr(fail), max_iter,
+                                           {"peel": MODE_PEEL, "hybrid": MODE_HYBRID}[mode], B, _stream()))
+        return out, fail
+
+
 class RsCodec:
     """Reed-Solomon GF(2^8) erasure codec (rs_ctx): field 0x171, G[i][j] = alpha^(i*j) systematised,
     decode from the first k received symbols -- Matlab/ReedSolomonErasureCodes.m, Test_My_RS_Decode.m."""

@@ -23,6 +23,7 @@
 #include "hmat.hpp"
 #include "fec_packets.cuh"
 #include "hybrid_ge.cuh"
+#include "nb_ldpc.cuh"
 #include "payload_exec.cuh"
 #include "peel_schedule.cuh"
 #include "rs_gf256.cuh"
@@ -1189,6 +1190,212 @@ extern "C" int ldpc_encode_host_multi(ldpc_ctx *const *ctxs, int n_ctx, const vo
         const size_t in_cw = size_t(c->code.k) * c->S, out_cw = size_t(c->code.n) * c->S;
         return ldpc_encode_host(c, static_cast<const uint8_t *>(h_info) + size_t(b0) * in_cw, static_cast<uint8_t *>(h_cw) + size_t(b0) * out_cw, nb);
     });
+}
+
+
+// ------------------------------------------------------------------------------------------
+// non-binary GF(256) LDPC code: Matlab/ErasureCodes_NonBinaryLDPCSim.m,
+// Matlab/My_LDPC_HybridML_NonBinary_Erasure_Decoder.m.  The structure (and with it the peeling
+// schedule) is the binary context's; this context adds one nonzero field element per edge.
+// ------------------------------------------------------------------------------------------
+struct ldpc_nb_ctx {
+    ldpc_ctx *base = nullptr;
+    std::vector<uint8_t> coef_csr;          // one coefficient per nonzero of H, CSR order
+    uint8_t *d_coef = nullptr;              // [m][RW], pad 0
+    uint8_t *d_tab = nullptr;               // log[256] | alog[512]
+    uint32_t *d_m8 = nullptr;               // [256][8]
+    uint8_t *d_enc_blob = nullptr;          // the encoder's static schedule
+    int enc_blob_bytes = 0;
+    int W = 0;                              // slice bytes of nb_exec_kernel (32, or 16 when S is not a multiple of 32)
+    int smem_dec = 0, smem_enc = 0;
+    // hybrid mode
+    long long work_batch = 0;
+    uint8_t *d_work = nullptr;              // [work_batch][n][S]
+    unsigned int *d_list = nullptr, *d_count = nullptr;
+    uint8_t *d_gA = nullptr, *d_gB = nullptr;
+    int ge_grid = 0, ge_smem = 0;
+};
+
+static void nb_free(ldpc_nb_ctx *c)
+{
+    if (!c) return;
+    if (c->base) cudaSetDevice(c->base->device);
+    cudaFree(c->d_coef); cudaFree(c->d_tab); cudaFree(c->d_m8); cudaFree(c->d_enc_blob); cudaFree(c->d_work);
+    cudaFree(c->d_list); cudaFree(c->d_count); cudaFree(c->d_gA); cudaFree(c->d_gB);
+    delete c;
+}
+
+extern "C" int ldpc_nb_ctx_create(ldpc_nb_ctx **out, ldpc_ctx *base, const uint8_t *coef_csr, uint32_t coef_seed)
+{
+    if (!out || !base) return fail(LDPC_ERR_ARG, "NULL argument to ldpc_nb_ctx_create");
+    *out = nullptr;
+    const HostCode &code = base->code;
+    ldpc_nb_ctx *c = new (std::nothrow) ldpc_nb_ctx();
+    if (!c) return fail(LDPC_ERR_NOMEM, "out of host memory");
+    c->base = base;
+    c->coef_csr.resize(size_t(code.nnz));
+    if (coef_csr) {
+        for (int e = 0; e < code.nnz; e++) {
+            if (!coef_csr[e]) { delete c; return fail(LDPC_ERR_ARG, "a coefficient of the non-binary code is zero"); }
+            c->coef_csr[size_t(e)] = coef_csr[e];
+        }
+    } else {
+        // floor((GF_SIZE-1)*rand)+1 (sim :55), drawn with Threefry4x32-20: key {3, seed}, counter = index of the nonzero
+        for (int e = 0; e < code.nnz; e++) {
+            const uint32_t ctr[4] = {uint32_t(e), 0u, 0u, 0u}, key[4] = {3u, coef_seed, 0u, 0u};
+            uint32_t r[4];
+            threefry4x32_20(ctr, key, r);
+            c->coef_csr[size_t(e)] = uint8_t(1u + r[0] % 255u);
+        }
+    }
+    std::vector<uint8_t> coef(size_t(code.m) * code.RW, 0);
+    for (int r = 0; r < code.m; r++)
+        for (int j = code.row_ptr[r]; j < code.row_ptr[r + 1]; j++) coef[size_t(r) * code.RW + (j - code.row_ptr[r])] = c->coef_csr[size_t(j)];
+    uint8_t tab[768];
+    rs_host_tables(tab, tab + 256);
+    std::vector<uint32_t> m8(256 * 8);
+    for (int v = 0; v < 256; v++) for (int j = 0; j < 8; j++) m8[size_t(v * 8 + j)] = ((v >> j) & 1) ? 0xFFFFFFFFu : 0u;
+    const std::vector<uint8_t> blob = make_enc_blob(code, 16);
+    c->enc_blob_bytes = int((blob.size() + 15) & ~size_t(15));
+    c->W = base->S % 32 == 0 ? 32 : 16;
+    const int fixed = code.m * code.RW * 2 + ((code.m * code.RW + 15) & ~15) + 256 * 8 * 4 + 768;
+    c->smem_dec = code.n * c->W + fixed + sched_blob_max_bytes(code.m);
+    c->smem_enc = code.n * c->W + fixed + c->enc_blob_bytes;
+    if (std::max(c->smem_dec, c->smem_enc) > base->smem_optin) { delete c; return fail(LDPC_ERR_UNSUPPORTED, "code too long for the non-binary executor's shared memory"); }
+    cudaError_t e = cudaSetDevice(base->device);
+    auto ok = [&](cudaError_t r) { if (e == cudaSuccess) e = r; return e == cudaSuccess; };
+    if (ok(cudaMalloc(&c->d_coef, coef.size())) && ok(cudaMemcpy(c->d_coef, coef.data(), coef.size(), cudaMemcpyHostToDevice)) &&
+        ok(cudaMalloc(&c->d_tab, 768)) && ok(cudaMemcpy(c->d_tab, tab, 768, cudaMemcpyHostToDevice)) &&
+        ok(cudaMalloc(&c->d_m8, m8.size() * 4)) && ok(cudaMemcpy(c->d_m8, m8.data(), m8.size() * 4, cudaMemcpyHostToDevice)) &&
+        ok(cudaMalloc(&c->d_list, size_t(base->max_batch) * 4)) && ok(cudaMalloc(&c->d_count, 16)) && !blob.empty()) {
+        std::vector<uint8_t> padded(size_t(c->enc_blob_bytes), 0);
+        memcpy(padded.data(), blob.data(), blob.size());
+        if (ok(cudaMalloc(&c->d_enc_blob, padded.size()))) ok(cudaMemcpy(c->d_enc_blob, padded.data(), padded.size(), cudaMemcpyHostToDevice));
+    }
+    if (e != cudaSuccess) { nb_free(c); return fail(e == cudaErrorMemoryAllocation ? LDPC_ERR_NOMEM : LDPC_ERR_CUDA, std::string("ldpc_nb_ctx_create: ") + cudaGetErrorString(e)); }
+    *out = c;
+    return LDPC_OK;
+}
+
+extern "C" int ldpc_nb_ctx_destroy(ldpc_nb_ctx *c)
+{
+    nb_free(c);
+    return LDPC_OK;
+}
+
+extern "C" int ldpc_nb_get_coefficients(const ldpc_nb_ctx *c, uint8_t *coef_csr)
+{
+    if (!c || !coef_csr) return fail(LDPC_ERR_ARG, "NULL argument");
+    memcpy(coef_csr, c->coef_csr.data(), c->coef_csr.size());
+    return LDPC_OK;
+}
+
+static int nb_launch_exec(ldpc_nb_ctx *c, const void *d_in, int rows_in, void *d_out, int rows_out, const uint8_t *sched, int sched_stride,
+                          int sched_max, int smem, long long B, cudaStream_t st)
+{
+    ldpc_ctx *b = c->base;
+    NbExecParams p;
+    p.in = static_cast<const uint8_t *>(d_in); p.out = static_cast<uint8_t *>(d_out); p.sched = sched; p.cidx = b->d_cidx; p.coef = c->d_coef;
+    p.tab = c->d_tab; p.m8 = c->d_m8; p.B = B; p.sched_stride = sched_stride; p.sched_max = sched_max; p.n = b->code.n; p.m = b->code.m;
+    p.RW = b->code.RW; p.S = b->S; p.rows_in = rows_in; p.rows_out = rows_out; p.slices = b->S / c->W;
+    const int per_sm = std::max(1, b->smem_optin / (smem + 1024));
+    const int grid = int(std::min<long long>(B * p.slices, (long long)b->num_sms * per_sm));
+    auto k = c->W == 32 ? nb_exec_kernel<32> : nb_exec_kernel<16>;
+    int rc = allow_max_smem(reinterpret_cast<const void *>(k), b->smem_optin);
+    if (rc) return rc;
+    {
+        ProfScope ps(b, sched_stride ? LDPC_K_EXEC_DECODE : LDPC_K_EXEC_ENCODE, st);
+        k<<<grid, kNbThreads, smem, st>>>(p);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return debug_sync("nb_exec_kernel", st);
+}
+
+extern "C" int ldpc_nb_encode(ldpc_nb_ctx *c, const void *d_info, void *d_cw, int64_t B, void *stream)
+{
+    if (!c || B < 0) return fail(LDPC_ERR_ARG, "bad argument to ldpc_nb_encode");
+    if (B == 0) return LDPC_OK;
+    if (!d_info || !d_cw) return fail(LDPC_ERR_ARG, "NULL buffer passed to ldpc_nb_encode");
+    if (!c->base->code.triangular) return fail(LDPC_ERR_NOT_TRIANGULAR, "H is not in triangular form (last entry of row r must be column k + r)");
+    CUDA_TRY(cudaSetDevice(c->base->device));
+    return nb_launch_exec(c, d_info, c->base->code.k, d_cw, c->base->code.n, c->d_enc_blob, 0, c->enc_blob_bytes, c->smem_enc, B,
+                          static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int ldpc_nb_decode(ldpc_nb_ctx *c, const void *d_cw, const uint32_t *d_mask, void *d_out, uint8_t *d_fail, int max_iter,
+                              int mode, int64_t B, void *stream)
+{
+    if (!c || B < 0) return fail(LDPC_ERR_ARG, "bad argument to ldpc_nb_decode");
+    if (B == 0) return LDPC_OK;
+    if (!d_cw || !d_mask || !d_out) return fail(LDPC_ERR_ARG, "NULL buffer passed to ldpc_nb_decode");
+    if (mode != LDPC_MODE_PEEL && mode != LDPC_MODE_HYBRID) return fail(LDPC_ERR_ARG, "unknown decode mode");
+    if (max_iter < 0 || max_iter > 1000000) return fail(LDPC_ERR_ARG, "max_iter out of range");
+    ldpc_ctx *b = c->base;
+    CUDA_TRY(cudaSetDevice(b->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t in_cw = size_t(b->code.n) * b->S, out_cw = size_t(b->code.k) * b->S;
+    long long chunk = b->max_batch;
+    if (mode == LDPC_MODE_HYBRID) {
+        if (!c->d_work) {      // first hybrid call: the work buffer (whole codewords after the sweeps) and the elimination workspaces
+            c->work_batch = std::max<long long>(1, std::min<long long>(b->max_batch, (1ll << 30) / (long long)in_cw));
+            c->ge_grid = b->num_sms;
+            c->ge_smem = 768 + b->NW * 4 + ((b->NW + 1) & ~1) * 2 + ((b->code.m + 3) & ~3) + 3 * b->code.m * 2 + 64;
+            cudaError_t e = cudaSuccess;
+            auto ok = [&](cudaError_t r) { if (e == cudaSuccess) e = r; return e == cudaSuccess; };
+            if (!(ok(cudaMalloc(&c->d_work, size_t(c->work_batch) * in_cw)) && ok(cudaMalloc(&c->d_gA, size_t(c->ge_grid) * b->code.m * b->code.m)) &&
+                  ok(cudaMalloc(&c->d_gB, size_t(c->ge_grid) * b->code.m * b->S)))) {
+                cudaFree(c->d_work); cudaFree(c->d_gA); cudaFree(c->d_gB);
+                c->d_work = nullptr; c->d_gA = nullptr; c->d_gB = nullptr;
+                return fail(LDPC_ERR_NOMEM, std::string("non-binary hybrid scratch: ") + cudaGetErrorString(e));
+            }
+        }
+        chunk = c->work_batch;
+    }
+    for (long long b0 = 0; b0 < B; b0 += chunk) {
+        const long long nb = std::min<long long>(chunk, B - b0);
+        const uint8_t *cw = static_cast<const uint8_t *>(d_cw) + size_t(b0) * in_cw;
+        const uint32_t *mask = d_mask + size_t(b0) * b->NW;
+        uint8_t *out = static_cast<uint8_t *>(d_out) + size_t(b0) * out_cw;
+        uint8_t *failp = d_fail ? d_fail + b0 : b->d_fail_scratch;
+        // pattern phase: the binary code's peel kernel (the schedule does not depend on the coefficients)
+        PeelParams pp;
+        pp.mask = mask; pp.sched = b->d_sched; pp.sched_len = b->d_sched_len; pp.work_ctr = b->d_work_ctr; pp.fail = failp; pp.fail_any = nullptr;
+        pp.resid = b->d_resid; pp.stats = b->d_stats; pp.cidx = b->d_cidx; pp.vadj = b->d_vadj; pp.B = nb; pp.n = b->code.n; pp.k = b->code.k;
+        pp.m = b->code.m; pp.RW = b->code.RW; pp.VW = b->code.VW; pp.NW = b->NW; pp.MW = b->MW; pp.stride = b->sched_stride; pp.max_iter = max_iter;
+        pp.rs_n = b->rs_n; pp.rs_k = b->rs_k; pp.groups_per_block = b->peel_groups; pp.count_stats = 1;
+        pp.ge_list = nullptr; pp.ge_count = nullptr;
+        if (mode == LDPC_MODE_HYBRID) {
+            CUDA_TRY(cudaMemsetAsync(c->d_count, 0, 16, st));
+            pp.ge_list = c->d_list; pp.ge_count = c->d_count;
+        }
+        CUDA_TRY(cudaMemsetAsync(pp.work_ctr, 0, sizeof(unsigned int), st));
+        {
+            ProfScope ps(b, LDPC_K_PEEL, st);
+            const int grid = int(std::min<long long>(b->num_sms, (nb + b->peel_groups - 1) / b->peel_groups));
+            pick_peel(b->MW, b->code.VW)<<<grid, b->peel_groups * b->peel_G, b->peel_smem, st>>>(pp);
+        }
+        CUDA_TRY(cudaGetLastError());
+        // payload phase
+        const bool hyb = mode == LDPC_MODE_HYBRID;
+        int rc = nb_launch_exec(c, cw, b->code.n, hyb ? static_cast<void *>(c->d_work) : static_cast<void *>(out), hyb ? b->code.n : b->code.k,
+                                b->d_sched, b->sched_stride, sched_blob_max_bytes(b->code.m), c->smem_dec, nb, st);
+        if (rc) return rc;
+        if (hyb) {
+            NbGeParams gp;
+            gp.work = c->d_work; gp.mask = mask; gp.sched = b->d_sched; gp.list = c->d_list; gp.list_count = c->d_count; gp.fail = failp;
+            gp.stats = b->d_stats; gp.cidx = b->d_cidx; gp.coef = c->d_coef; gp.tab = c->d_tab; gp.gA = c->d_gA; gp.gB = c->d_gB;
+            gp.n = b->code.n; gp.k = b->code.k; gp.m = b->code.m; gp.RW = b->code.RW; gp.NW = b->NW; gp.S = b->S; gp.stride = b->sched_stride;
+            {
+                ProfScope ps(b, LDPC_K_HYBRID_CTA, st);
+                nb_ge_kernel<<<c->ge_grid, kNbThreads, c->ge_smem, st>>>(gp);
+            }
+            CUDA_TRY(cudaGetLastError());
+            CUDA_TRY(cudaMemcpy2DAsync(out, out_cw, c->d_work, in_cw, out_cw, size_t(nb), cudaMemcpyDeviceToDevice, st));
+            int rcd = debug_sync("nb_ge_kernel", st);
+            if (rcd) return rcd;
+        }
+    }
+    return LDPC_OK;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -704,3 +704,184 @@ int orc_ready_to_decode(int n, int k, int cur_cnt, int next_cnt)
     const int desired = (int)((double)m * 0.8 + 0.5), minimum = (int)((double)m * 0.2 + 0.5);   /* round() */
     return (cur_cnt == n) || ((cur_cnt > k + desired) && (next_cnt > 10)) || ((cur_cnt > k + minimum) && (next_cnt > 100));
 }
+
+/* ------------------------------------------------------------------------- */
+/* Non-binary GF(256) LDPC code.                         */
+/*   coefficients: Matlab/ErasureCodes_NonBinaryLDPCSim.m:51-58 -- the binary  */
+/*     H keeps its structure, every 1 becomes floor((GF_SIZE-1)*rand)+1, i.e.  */
+/*     a nonzero field element.  MATLAB's rand stream is not reproducible, so  */
+/*     the draw is Threefry4x32-20, key {3, seed, 0, 0}, counter {e, 0, 0, 0}  */
+/*     for the e-th nonzero of H in row-major (CSR) order: 1 + (v[0] mod 255)  */
+/*     (an extension in the spirit of the erasure generator; the CUDA path     */
+/*     uses the same draw, or any table the caller supplies);                  */
+/*   encoder: :176-182 -- parity p = inv(h_diag) * sum_{others} h * c;         */
+/*   decoder: Matlab/My_LDPC_HybridML_NonBinary_Erasure_Decoder.m -- <= itenum */
+/*     serial sweeps (:19-55: a check with ONE erased member recovers it as    */
+/*     inv(h) * sum of h * y over the others), then Gauss-Jordan over GF(256)  */
+/*     on the residual set (:57-125), field polynomial 0x171 (:69 of the sim). */
+/* A symbol is S bytes; the check's coefficient multiplies every byte.         */
+/* ------------------------------------------------------------------------- */
+void orc_nb_coefficients(int64_t nnz, uint32_t seed, uint8_t *coef)
+{
+    for (int64_t e = 0; e < nnz; e++) {
+        const uint32_t ctr[4] = {(uint32_t)e, (uint32_t)(e >> 32), 0u, 0u}, key[4] = {3u, seed, 0u, 0u};
+        uint32_t out[4];
+        orc_threefry4x32_20(ctr, key, out);
+        coef[e] = (uint8_t)(1u + out[0] % 255u);
+    }
+}
+
+static void nb_axpy(uint8_t *dst, const uint8_t *src, uint8_t a, int S)   /* dst += a * src */
+{
+    if (a == 0) return;
+    const int la = gf_log_t[a];
+    for (int l = 0; l < S; l++)
+        if (src[l]) dst[l] ^= gf_alog_t[la + gf_log_t[src[l]]];
+}
+
+static void nb_scale(uint8_t *dst, uint8_t a, int S)                      /* dst *= a */
+{
+    const int la = gf_log_t[a];
+    for (int l = 0; l < S; l++) dst[l] = (dst[l] && a) ? gf_alog_t[la + gf_log_t[dst[l]]] : 0;
+}
+
+void orc_nb_encode(int n, int k, const int32_t *row_ptr, const int32_t *col_idx, const uint8_t *coef, int S,
+                   const uint8_t *info, uint8_t *cw)
+{
+    gf_init();
+    memcpy(cw, info, (size_t)k * S);
+    for (int r = 0; r < n - k; r++) {
+        uint8_t *p = cw + (size_t)(k + r) * S;
+        memset(p, 0, (size_t)S);
+        const int last = row_ptr[r + 1] - 1;                   /* the diagonal: not used in the sum (sim :178) */
+        for (int j = row_ptr[r]; j < last; j++) nb_axpy(p, cw + (size_t)col_idx[j] * S, coef[j], S);
+        nb_scale(p, gf_inv(coef[last]), S);                    /* :181 */
+    }
+}
+
+/* One codeword in place.  Returns 0 = clean after the sweeps, 1 = elimination ran and succeeded, 2 = it met a
+ * column without pivot (ml_fail: the state after the sweeps is left, as for the binary hybrid decoder);
+ * do_ml = 0 stops after the sweeps (returns 0 / 3 = erasures left).  *iters = sweeps made.                       */
+int orc_nb_hybrid(int n, int k, const int32_t *row_ptr, const int32_t *col_idx, const uint8_t *coef, int S,
+                  uint8_t *payload, uint8_t *erased, int peel_iter, int do_ml, int *iters)
+{
+    gf_init();
+    const int m = n - k;
+    int it = 0, left = 0;
+    for (int i = 0; i < n; i++) left += erased[i] ? 1 : 0;
+    uint8_t *acc = (uint8_t *)malloc((size_t)S);
+    while (left > 0 && it < peel_iter) {                       /* decoder :19-55 */
+        it++;
+        for (int c = 0; c < m; c++) {
+            int cnt = 0, at = -1;
+            for (int j = row_ptr[c]; j < row_ptr[c + 1]; j++)
+                if (erased[col_idx[j]]) { cnt++; at = j; }
+            if (cnt != 1) continue;
+            memset(acc, 0, (size_t)S);
+            for (int j = row_ptr[c]; j < row_ptr[c + 1]; j++)
+                if (j != at) nb_axpy(acc, payload + (size_t)col_idx[j] * S, coef[j], S);
+            nb_scale(acc, gf_inv(coef[at]), S);
+            memcpy(payload + (size_t)col_idx[at] * S, acc, (size_t)S);
+            erased[col_idx[at]] = 0;
+            left--;
+        }
+    }
+    free(acc);
+    if (iters) *iters = it;
+    if (left == 0) return 0;
+    if (!do_ml) return 3;
+
+    const int e = left;
+    int *E = (int *)malloc(sizeof(int) * (size_t)e);
+    int *pos = (int *)malloc(sizeof(int) * (size_t)n);
+    for (int i = 0, j = 0; i < n; i++) {
+        pos[i] = -1;
+        if (erased[i]) { pos[i] = j; E[j++] = i; }
+    }
+    uint8_t *A = (uint8_t *)calloc((size_t)m * (size_t)e, 1);      /* find_inv = H_sparse(:, erasure_ind) (:60) */
+    uint8_t *rhs = (uint8_t *)calloc((size_t)m * (size_t)S, 1);    /* :68-77 */
+    for (int c = 0; c < m; c++)
+        for (int j = row_ptr[c]; j < row_ptr[c + 1]; j++) {
+            const int u = col_idx[j];
+            if (pos[u] >= 0) A[(size_t)c * e + pos[u]] = coef[j];
+            else nb_axpy(rhs + (size_t)c * S, payload + (size_t)u * S, coef[j], S);
+        }
+    int abort_ml = e > m;
+    uint8_t *tmp = (uint8_t *)malloc((size_t)(e > S ? e : S));
+    for (int col = 0; col < e && !abort_ml; col++) {               /* :80-110 */
+        int first = -1;
+        for (int r = col; r < m; r++)
+            if (A[(size_t)r * e + col]) { first = r; break; }
+        if (first < 0) { abort_ml = 1; break; }
+        if (first != col) {
+            memcpy(tmp, rhs + (size_t)col * S, (size_t)S);
+            memcpy(rhs + (size_t)col * S, rhs + (size_t)first * S, (size_t)S);
+            memcpy(rhs + (size_t)first * S, tmp, (size_t)S);
+            memcpy(tmp, A + (size_t)col * e, (size_t)e);
+            memcpy(A + (size_t)col * e, A + (size_t)first * e, (size_t)e);
+            memcpy(A + (size_t)first * e, tmp, (size_t)e);
+        }
+        const uint8_t inv = gf_inv(A[(size_t)col * e + col]);      /* :92-98 make the diagonal 1 */
+        nb_scale(A + (size_t)col * e, inv, e);
+        nb_scale(rhs + (size_t)col * S, inv, S);
+        for (int r = first + 1; r < m; r++) {                      /* :100-108 the other rows that had a nonzero here */
+            if (r == col) continue;
+            const uint8_t f = A[(size_t)r * e + col];
+            if (!f) continue;
+            nb_axpy(A + (size_t)r * e, A + (size_t)col * e, f, e);
+            nb_axpy(rhs + (size_t)r * S, rhs + (size_t)col * S, f, S);
+        }
+    }
+    if (!abort_ml)
+        for (int col = e - 1; col >= 1; col--)                     /* :112-122 */
+            for (int r = 0; r < col; r++) {
+                const uint8_t f = A[(size_t)r * e + col];
+                if (!f) continue;
+                nb_axpy(rhs + (size_t)r * S, rhs + (size_t)col * S, f, S);
+                A[(size_t)r * e + col] = 0;
+            }
+    if (!abort_ml)
+        for (int j = 0; j < e; j++) {                              /* :124 */
+            memcpy(payload + (size_t)E[j] * S, rhs + (size_t)j * S, (size_t)S);
+            erased[E[j]] = 0;
+        }
+    free(tmp); free(rhs); free(A); free(pos); free(E);
+    return abort_ml ? 2 : 1;
+}
+
+void orc_nb_encode_batch(int n, int k, const int32_t *row_ptr, const int32_t *col_idx, const uint8_t *coef, int S,
+                         int64_t B, const uint8_t *info, uint8_t *cw, int nthreads)
+{
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+    gf_init();
+#pragma omp parallel for schedule(static)
+    for (int64_t b = 0; b < B; b++)
+        orc_nb_encode(n, k, row_ptr, col_idx, coef, S, info + (size_t)b * k * S, cw + (size_t)b * n * S);
+}
+
+void orc_nb_decode_batch(int n, int k, const int32_t *row_ptr, const int32_t *col_idx, const uint8_t *coef, int S,
+                         int64_t B, uint8_t *payload, uint8_t *erased, uint8_t *out, uint8_t *fail_sys,
+                         int32_t *iters, int32_t *status, int max_iter, int mode, int nthreads)
+{
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+    gf_init();
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int64_t b = 0; b < B; b++) {
+        uint8_t *p = payload + (size_t)b * n * S;
+        uint8_t *e = erased + (size_t)b * n;
+        int it = 0;
+        const int st = orc_nb_hybrid(n, k, row_ptr, col_idx, coef, S, p, e, max_iter, mode == 1, &it);
+        if (out) memcpy(out + (size_t)b * k * S, p, (size_t)k * S);
+        if (fail_sys) {
+            int f = 0;
+            for (int i = 0; i < k; i++) f |= e[i];
+            fail_sys[b] = (uint8_t)f;
+        }
+        if (iters) iters[b] = it;
+        if (status) status[b] = st;
+    }
+}

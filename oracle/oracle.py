@@ -228,3 +228,37 @@ def ready_to_decode(n, k, cur_cnt, next_cnt) -> bool:
 
 def num_threads():
     return lib().orc_num_threads()
+
+
+# ---- non-binary GF(256) LDPC code ---------------------------------------------------
+def nb_coefficients(code: Code, seed: int) -> np.ndarray:
+    """One nonzero GF(256) coefficient per nonzero of H in CSR order (ErasureCodes_NonBinaryLDPCSim.m:51-58, seeded)."""
+    coef = np.zeros(len(code.col_idx), dtype=np.uint8)
+    lib().orc_nb_coefficients(C.c_int64(len(coef)), C.c_uint32(seed & 0xFFFFFFFF), _p(coef))
+    return coef
+
+
+def nb_encode(code: Code, coef: np.ndarray, info: np.ndarray, nthreads=0) -> np.ndarray:
+    info = np.ascontiguousarray(info, dtype=np.uint8)
+    B, k, S = info.shape
+    assert k == code.k
+    cw = np.zeros((B, code.n, S), dtype=np.uint8)
+    lib().orc_nb_encode_batch(C.c_int(code.n), C.c_int(code.k), _p(code.row_ptr), _p(code.col_idx), _p(np.ascontiguousarray(coef)),
+                              C.c_int(S), C.c_int64(B), _p(info), _p(cw), C.c_int(nthreads))
+    return cw
+
+
+def nb_decode(code: Code, coef: np.ndarray, payload: np.ndarray, erased: np.ndarray, max_iter=10, mode="hybrid", nthreads=0):
+    """My_LDPC_HybridML_NonBinary_Erasure_Decoder.m.  status: 0 clean after the sweeps, 1 elimination succeeded,
+    2 elimination met a column without pivot, 3 (mode peel) erasures left."""
+    payload = np.array(payload, dtype=np.uint8, order="C")
+    erased = np.array(erased, dtype=np.uint8, order="C")
+    B, n, S = payload.shape
+    out = np.zeros((B, code.k, S), dtype=np.uint8)
+    fail = np.zeros(B, dtype=np.uint8)
+    iters = np.zeros(B, dtype=np.int32)
+    status = np.zeros(B, dtype=np.int32)
+    lib().orc_nb_decode_batch(C.c_int(code.n), C.c_int(code.k), _p(code.row_ptr), _p(code.col_idx), _p(np.ascontiguousarray(coef)),
+                              C.c_int(S), C.c_int64(B), _p(payload), _p(erased), _p(out), _p(fail), _p(iters), _p(status),
+                              C.c_int(max_iter), C.c_int({"peel": 0, "hybrid": 1}[mode]), C.c_int(nthreads))
+    return dict(out=out, payload=payload, erased=erased, fail_sys=fail, iters=iters, status=status)
