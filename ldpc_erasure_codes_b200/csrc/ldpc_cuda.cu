@@ -75,6 +75,10 @@ static int ge_stage_mask() { const char *e = getenv("LDPC_CUDA_GE_STAGES"); retu
 // LDPC_CUDA_TMA4=0: the executor moves its slots box by box (3-D tensor copies only)
 static const bool g_tma4 = [] { const char *e = getenv("LDPC_CUDA_TMA4"); return !(e && *e == '0'); }();
 
+// LDPC_CUDA_EXEC_PLAIN=1: the executor applies per-codeword schedules level by level with full-row gathers (the form it
+// falls back to when a blob leaves no room for its pass table; tests compare it with the bulk + walk form)
+static bool exec_plain() { const char *e = getenv("LDPC_CUDA_EXEC_PLAIN"); return e && *e && *e != '0'; }
+
 // LDPC_CUDA_DEBUG_SYNC=1: synchronise after every launch so that a faulting kernel is named
 static int debug_sync(const char *what, cudaStream_t st)
 {
@@ -278,7 +282,9 @@ static int choose_geom(const ldpc_ctx *c, bool dynamic_sched, ExecGeom *g)
         if (c->force_W && W != c->force_W) continue;
         const int slot = nbox * kBoxRows * W + kExecZeroRowBytes;
         if ((slot - kExecZeroRowBytes) / 16 > 0xFFFF) continue;   // check rows are staged as 16-bit offsets in 16-byte units
-        const int blob_min = dynamic_sched ? sched_area_bytes(m, std::min(m, 64)) : int(make_enc_blob(c->code, 32 / (W / 16)).size());
+        // (a per-codeword blob must fit whole; the executor's pass table and records take what is left of the area, and a
+        //  blob that leaves no room for its pass table is applied in the plain level-by-level form)
+        const int blob_min = dynamic_sched ? sched_blob_max_bytes(m) : int(make_enc_blob(c->code, 32 / (W / 16)).size());
         const int blob_max = dynamic_sched ? sched_area_bytes(m, m) : blob_min;
         int nslot;
         if (dynamic_sched) nslot = (c->smem_optin - fixed) / (slot + blob_min);
@@ -596,7 +602,7 @@ static int launch_exec(ldpc_ctx *c, const ExecGeom &g, const void *d_in, int row
     p.sched_max = g.sched_area; p.m = c->code.m; p.RW = c->code.RW; p.rows_in = rows_in; p.rows_out = rows_out;
     p.nbox_in = (rows_in + kBoxRows - 1) / kBoxRows; p.nbox_out = (rows_out + kBoxRows - 1) / kBoxRows;
     p.slices = c->S / g.W; p.nslot = g.nslot; p.slot_bytes = g.slot_bytes;
-    p.zrow = sched_zero_row(c->code.n); p.out = static_cast<uint8_t *>(d_out); p.S = c->S; p.n = c->code.n; p.msk_words = g.msk_words;
+    p.zrow = sched_zero_row(c->code.n); p.out = static_cast<uint8_t *>(d_out); p.S = c->S; p.n = c->code.n; p.msk_words = g.msk_words; p.force_plain = exec_plain() ? 1 : 0;
     p.phase_cycles = sched_stride ? c->d_phase : nullptr;
     int rwm = 0;
     ExecKernel k = pick_exec(g.W, c->code.max_row_weight, &rwm);

@@ -77,6 +77,7 @@ struct ExecParams {
     const uint32_t *mask;       // per-codeword schedules: [B][NW] erasure masks
     int NW, n;
     int msk_words;              // mask words per slot: covers the bits of the zero rows behind the slot
+    int force_plain;            // test aid: per-codeword schedules are applied in the plain level-by-level form, always
     uint8_t *out;               // [B][rows_out][S]: the output the tensor maps describe (the walk's symbols are re-stored with plain stores)
     int S;
     int nfull_in, nfull_out;    // whole 256-row boxes moved by ONE 4-D tensor copy (map [B][rows/256][256][S]); the rest box by box
@@ -253,6 +254,7 @@ payload_exec_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
         lap(0);
         const uint32_t *hdr = reinterpret_cast<const uint32_t *>(blob);
         int ne, nl, nrec, npass, n1;
+        bool simple = false;               // no room for the pass table next to this blob: plain level-by-level form
         const uint32_t *ent;
         const uint16_t *lvo;
         uint32_t pt_a, rec_a;              // shared-space addresses of the pass table and the records
@@ -271,6 +273,7 @@ payload_exec_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
             lvo = reinterpret_cast<const uint16_t *>(ent + ne);
             n1 = nl >= 2 ? int(lvo[1]) : ne;   // entries of the first level: no produced members, no record
             pt_a = smem_u32(lvo) + 2u * uint32_t(nl + 1);
+            const uint32_t area_end = smem_u32(blob) + uint32_t(p.sched_max);
             // passes: level index L = 1 .. nl-1 covers entries [lvo[L], lvo[L+1]), cut into pieces of <= EPW
             // (every warp computes the count; warp 0 writes the table: first entry | (count - 1) << 11)
             npass = 0;
@@ -286,15 +289,16 @@ payload_exec_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
                 }
                 if (wg == 0) {
                     uint32_t at = pt_a + 2u * uint32_t(npass + inc - np);
-                    for (int pos = s0; pos < s1; pos += EPW, at += 2u) {
+                    for (int pos = s0; pos < s1 && at + 2u <= area_end; pos += EPW, at += 2u) {
                         const unsigned short pw = (unsigned short)(pos | ((min(EPW, s1 - pos) - 1) << 11));
                         asm volatile("st.shared.u16 [%0], %1;" ::"r"(at), "h"(pw) : "memory");
                     }
                 }
                 npass += __shfl_sync(0xFFFFFFFFu, inc, 31);
             }
+            simple = p.force_plain || pt_a + 2u * uint32_t(npass) > area_end;     // (a blob near its maximum size in an area sized for it alone)
             rec_a = (pt_a + 2u * uint32_t(npass) + 7u) & ~7u;
-            const int room = (int(smem_u32(blob)) + p.sched_max - int(rec_a)) / 8;
+            const int room = simple ? 0 : (int(area_end) - int(rec_a)) / 8;
             nrec = max(0, min(ne - n1, room));
             // records: the members of the entry's check that were erased on arrival, the target excepted
             const unsigned long long z = (unsigned long long)uint32_t(p.zrow);
@@ -344,8 +348,28 @@ payload_exec_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
         }
         named_bar_sync(bar_id, GT);
 
+        if (simple) {
+            // plain form: level by level, every entry gathers ALL members of its check (its own row reads as zero), a
+            // barrier of the group between two levels
+            for (int L = 0; L < nl; L++) {
+                for (int i = int(lvo[L]) + eslot; i < int(lvo[L + 1]); i += NGROUPS) {
+                    const uint32_t e = ent[i];
+                    uint32_t rr[RWQ * 4];
+                    load_row(e >> 16, rr);
+                    uint4 acc = z4;
+#pragma unroll
+                    for (int t = 0; t < SL; t++) {
+                        const uint32_t o16 = (t & 1) ? (rr[t >> 1] >> 16) : (rr[t >> 1] & 0xFFFFu);
+                        xor_acc(acc, lds128(base_a + (o16 << 4)));
+                    }
+                    sts128(base_a + ((e & 0xFFFFu) << W_SH), acc);
+                }
+                named_bar_sync(bar_id, GT);
+            }
+            npass = 0;
+        }
         // ---- 1. bulk: s_i = XOR of the check's received members, records of the produced ones --------
-        for (int hi = ne; hi > 0; hi -= R * NGROUPS) {
+        for (int hi = simple ? 0 : ne; hi > 0; hi -= R * NGROUPS) {
             uint4 res[R];
             uint32_t va[R];
 #pragma unroll

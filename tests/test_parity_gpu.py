@@ -414,6 +414,19 @@ def test_hybrid_decode_bit_exact(codecs, P):
         assert (ref["status"] == 1).sum() > 20      # the elimination stage really ran and succeeded
 
 
+@pytest.mark.parametrize("mode,it", [("peel", 50), ("hybrid", 10)])
+def test_executor_plain_form_matches(monkeypatch, mode, it):
+    """The executor's fallback for a blob that leaves no room for its pass table (plain level-by-level gathers), forced."""
+    from ldpc_erasure_codes_b200.codec import LdpcCodec
+    monkeypatch.setenv("LDPC_CUDA_EXEC_PLAIN", "1")
+    codec = LdpcCodec(code=1, symbol_bytes=64, device=0, max_batch=128)
+    code, cw, rx, mask, flags = _scenario(codec, 1, 150, 13, 91, 64)
+    out, fail = codec.decode(rx, mask, max_iter=it, mode=mode)
+    ref = orc.decode(code, _np(rx), flags, max_iter=it, mode=mode)
+    assert np.array_equal(_np(fail), ref["fail_sys"]) and np.array_equal(_np(out), ref["out"])
+    codec.close()
+
+
 def test_hybrid_batch_larger_than_small_max_batch():
     """A context created with max_batch < 256: hybrid chunks must not exceed it (the schedule scratch is sized for
     max_batch codewords -- a round-2 regression found by tools/sanitize_pass.py: illegal address)."""
