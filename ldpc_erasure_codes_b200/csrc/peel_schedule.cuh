@@ -252,6 +252,12 @@ __global__ void __launch_bounds__(1024) peel_schedule_kernel(const PeelParams p)
                 asm volatile("st.shared.u32 [%0], %1;" ::"r"(a2), "r"(nv) : "memory");
                 if (upd && !self && cnt2 == 1u)
                     asm volatile("red.shared.or.b32 [%0], %1;" ::"r"((int(c2) > c ? cur_a : nxt_a) + 4u * (c2 >> 5)), "r"(1u << (c2 & 31)) : "memory");
+                if (upd && !self && cnt2 == 0u) {
+                    // the check was pending and its last erased member has just been recovered by another check: it would be
+                    // popped later and do nothing (13 % of the pops at the threshold); its bit is in one of the two bitmaps
+                    asm volatile("red.shared.and.b32 [%0], %1;" ::"r"(cur_a + 4u * (c2 >> 5)), "r"(~(1u << (c2 & 31))) : "memory");
+                    asm volatile("red.shared.and.b32 [%0], %1;" ::"r"(nxt_a + 4u * (c2 >> 5)), "r"(~(1u << (c2 & 31))) : "memory");
+                }
             }
             // end of sweep: swap the bitmaps; stop at the cap or at the fixed point (two empty sweeps)
             sweep += swp ? 1 : 0;
