@@ -265,6 +265,31 @@ int ldpc_packetize(ldpc_ctx *ctx, const void *d_cw, uint32_t block0, int64_t B, 
 int ldpc_depacketize(ldpc_ctx *ctx, const void *d_packets, int64_t n_packets, uint32_t block0, int64_t B,
                      void *d_cw, uint32_t *d_mask, uint32_t *d_counts, void *stream);
 int ldpc_ready_to_decode(const ldpc_ctx *ctx, int cur_block_cnt, int next_block_cnt);
+/* Variable payload length (sender :162,186-197 `num_longs_used`; receiver :94-111): a packet still occupies an
+ * 8 + S byte slot; d_len8[packet] (<= S / 8) says how many 8-byte payload words are valid.  The sender zero-fills the
+ * rest of the slot, the receiver leaves the rest of the symbol zero.  d_len8 of ldpc_packetize_var is [B * n].       */
+int ldpc_packetize_var(ldpc_ctx *ctx, const void *d_cw, const uint16_t *d_len8, uint32_t block0, int64_t B, void *d_packets,
+                       void *stream);
+int ldpc_depacketize_var(ldpc_ctx *ctx, const void *d_packets, const uint16_t *d_len8, int64_t n_packets, uint32_t block0,
+                         int64_t B, void *d_cw, uint32_t *d_mask, uint32_t *d_counts, void *stream);
+/* The receiver's two-buffer state machine (ldpc_erasure_decoder_with_reordering_logic.cl:45-142): the first usable
+ * packet names the current block, the next block number (modulo 256) is assembled beside it, packets of any other
+ * block are dropped, and after EVERY packet the hand-off rule (ldpc_ready_to_decode) is evaluated on the two arrival
+ * counters; when it fires the current block is decoded as it stands and emitted, `next` becomes `current` and the freed
+ * buffer is cleared.  ldpc_rx_stream_push takes a batch of packets in arrival order ([n_packets][8 + S] on the device,
+ * d_len8 may be NULL), reads the headers back, runs that per-packet control on the host and the payload through
+ * ldpc_depacketize / ldpc_decode on the GPU; blocks that became ready are written to d_out [cap][k][S], d_fail [cap],
+ * h_blocks [cap] (host: their block numbers), *n_decoded of them (LDPC_ERR_ARG if more than cap).  ldpc_rx_stream_flush
+ * ends the stream: the current block, then the next if it holds packets, decoded as they stand.
+ * ldpc_rx_stream_state: {current, next, packets counted for current, for next}.  Synchronises `stream`.              */
+typedef struct ldpc_rx_stream ldpc_rx_stream;
+int ldpc_rx_stream_create(ldpc_rx_stream **out, ldpc_ctx *ctx, int max_iter, int mode);
+int ldpc_rx_stream_destroy(ldpc_rx_stream *s);
+int ldpc_rx_stream_push(ldpc_rx_stream *s, const void *d_packets, const uint16_t *d_len8, int64_t n_packets, void *d_out,
+                        uint8_t *d_fail, int32_t *h_blocks, int cap, int *n_decoded, void *stream);
+int ldpc_rx_stream_flush(ldpc_rx_stream *s, void *d_out, uint8_t *d_fail, int32_t *h_blocks, int cap, int *n_decoded,
+                         void *stream);
+int ldpc_rx_stream_state(const ldpc_rx_stream *s, int32_t state[4]);
 
 /* ---- Reed-Solomon GF(2^8) comparison code -------------------------------------------
  * Field polynomial 0x171, alpha = 2 (Matlab/Build_GF256_Lookup_Tables.m:11-24);

@@ -12,7 +12,7 @@ SO_PATH = os.path.join(HERE, "libldpc_cuda.so")
 EXPORTS = [
     "ldpc_ctx_create", "ldpc_ctx_destroy", "ldpc_ctx_info", "ldpc_read_h_file", "ldpc_ctx_get_csr", "ldpc_ctx_set_exec_geometry",
     "ldpc_encode", "ldpc_gen_erasures", "ldpc_decode", "ldpc_decode_ex", "ldpc_simulate_fer", "ldpc_get_stats", "ldpc_reset_stats",
-    "ldpc_encode_host", "ldpc_decode_host", "ldpc_decode_host_ex", "ldpc_encode_host_multi", "ldpc_decode_host_multi", "ldpc_fill_random", "ldpc_packetize", "ldpc_depacketize", "ldpc_ready_to_decode", "ldpc_profile_enable", "ldpc_profile_read",
+    "ldpc_encode_host", "ldpc_decode_host", "ldpc_decode_host_ex", "ldpc_encode_host_multi", "ldpc_decode_host_multi", "ldpc_fill_random", "ldpc_packetize", "ldpc_depacketize", "ldpc_ready_to_decode", "ldpc_packetize_var", "ldpc_depacketize_var", "ldpc_rx_stream_create", "ldpc_rx_stream_destroy", "ldpc_rx_stream_push", "ldpc_rx_stream_flush", "ldpc_rx_stream_state", "ldpc_profile_enable", "ldpc_profile_read",
     "rs_ctx_create", "rs_ctx_destroy", "rs_ctx_get_generator", "rs_encode", "rs_decode",
     "ldpc_nb_ctx_create", "ldpc_nb_ctx_destroy", "ldpc_nb_get_coefficients", "ldpc_nb_encode", "ldpc_nb_decode",
     "ldpc_h_generate", "ldpc_h_count_short_cycles", "ldpc_h_last_error_string",
@@ -84,6 +84,13 @@ def load():
     lib.ldpc_packetize.argtypes = [vp, vp, u32, i64, vp, vp]
     lib.ldpc_depacketize.argtypes = [vp, vp, i64, u32, i64, vp, vp, vp, vp]
     lib.ldpc_ready_to_decode.argtypes = [vp, i32, i32]
+    lib.ldpc_packetize_var.argtypes = [vp, vp, vp, u32, i64, vp, vp]
+    lib.ldpc_depacketize_var.argtypes = [vp, vp, vp, i64, u32, i64, vp, vp, vp, vp]
+    lib.ldpc_rx_stream_create.argtypes = [C.POINTER(vp), vp, i32, i32]
+    lib.ldpc_rx_stream_destroy.argtypes = [vp]
+    lib.ldpc_rx_stream_push.argtypes = [vp, vp, vp, i64, vp, vp, vp, i32, C.POINTER(i32), vp]
+    lib.ldpc_rx_stream_flush.argtypes = [vp, vp, vp, vp, i32, C.POINTER(i32), vp]
+    lib.ldpc_rx_stream_state.argtypes = [vp, C.POINTER(C.c_int32 * 4)]
     lib.ldpc_profile_enable.argtypes = [vp, i32]
     lib.ldpc_profile_read.argtypes = [vp, C.POINTER(Profile), i32]
     lib.rs_ctx_create.argtypes = [C.POINTER(vp), i32, i32, i32, i32, i64]

@@ -132,22 +132,33 @@ class LdpcCodec:
         return out, fail
 
     # ---- FEC packet front-ends (encoder_VITA_in_UDP_out.cl / decoder_with_reordering_logic.cl) ----
-    def packetize(self, cw: torch.Tensor, block0: int = 0) -> torch.Tensor:
-        """cw [B][n][S] -> packets [B*n][8+S]: 64-bit FEC header word [class|block|symbol] x2, then the symbol."""
+    def packetize(self, cw: torch.Tensor, block0: int = 0, len8: torch.Tensor | None = None) -> torch.Tensor:
+        """cw [B][n][S] -> packets [B*n][8+S]: 64-bit FEC header word [class|block|symbol] x2, then the symbol.
+        len8 [B*n] (int16, 8-byte words): variable payload length, the rest of a packet's slot is zero-filled."""
         assert cw.is_cuda and cw.dtype == torch.uint8 and cw.is_contiguous() and cw.shape[1:] == (self.n, self.S)
         B = cw.shape[0]
         pk = torch.empty((B * self.n, 8 + self.S), dtype=torch.uint8, device=cw.device)
-        _lib.check(self.lib.ldpc_packetize(self._h, _ptr(cw), block0 & 0xFFFFFFFF, B, _ptr(pk), _stream()))
+        if len8 is None:
+            _lib.check(self.lib.ldpc_packetize(self._h, _ptr(cw), block0 & 0xFFFFFFFF, B, _ptr(pk), _stream()))
+        else:
+            assert len8.is_cuda and len8.dtype == torch.int16 and len8.is_contiguous() and len8.numel() == B * self.n
+            _lib.check(self.lib.ldpc_packetize_var(self._h, _ptr(cw), _ptr(len8), block0 & 0xFFFFFFFF, B, _ptr(pk), _stream()))
         return pk
 
-    def depacketize(self, packets: torch.Tensor, block0: int, B: int):
-        """packets [N][8+S] in arrival order -> (cw [B][n][S], mask [B][mask_words], counts [B+1])."""
+    def depacketize(self, packets: torch.Tensor, block0: int, B: int, len8: torch.Tensor | None = None):
+        """packets [N][8+S] in arrival order -> (cw [B][n][S], mask [B][mask_words], counts [B+1]).
+        len8 [N] (int16): valid payload words per packet (the rest of the symbol stays zero)."""
         assert packets.is_cuda and packets.dtype == torch.uint8 and packets.is_contiguous() and packets.shape[1] == 8 + self.S
         cw = torch.empty((B, self.n, self.S), dtype=torch.uint8, device=packets.device)
         mask = torch.empty((B, self.mask_words), dtype=torch.int32, device=packets.device)
         counts = torch.empty((B + 1,), dtype=torch.int32, device=packets.device)
-        _lib.check(self.lib.ldpc_depacketize(self._h, _ptr(packets), packets.shape[0], block0 & 0xFFFFFFFF, B, _ptr(cw), _ptr(mask),
-                                             _ptr(counts), _stream()))
+        if len8 is None:
+            _lib.check(self.lib.ldpc_depacketize(self._h, _ptr(packets), packets.shape[0], block0 & 0xFFFFFFFF, B, _ptr(cw), _ptr(mask),
+                                                 _ptr(counts), _stream()))
+        else:
+            assert len8.is_cuda and len8.dtype == torch.int16 and len8.is_contiguous() and len8.numel() == packets.shape[0]
+            _lib.check(self.lib.ldpc_depacketize_var(self._h, _ptr(packets), _ptr(len8), packets.shape[0], block0 & 0xFFFFFFFF, B, _ptr(cw),
+                                                     _ptr(mask), _ptr(counts), _stream()))
         return cw, mask, counts
 
     def ready_to_decode(self, cur_block_cnt: int, next_block_cnt: int) -> bool:
@@ -257,6 +268,56 @@ def pack_mask(flags):
     pad = np.zeros((B, nw * 32), np.uint8)
     pad[:, :n] = flags
     return np.packbits(pad, axis=1, bitorder="little").view(np.uint32).astype(np.int32, copy=False).reshape(B, nw)
+
+
+class RxStream:
+    """The receiver's two-buffer state machine (ldpc_rx_stream; ldpc_erasure_decoder_with_reordering_logic.cl:45-142):
+    push packets in arrival order, get the blocks that became ready -- [(block number, out [k][S], fail)]."""
+
+    def __init__(self, codec: LdpcCodec, max_iter=50, mode="peel", cap=8):
+        self.lib = _lib.load()
+        self.codec = codec
+        self.cap = cap
+        h = C.c_void_p()
+        _lib.check(self.lib.ldpc_rx_stream_create(C.byref(h), codec._h, max_iter, {"peel": MODE_PEEL, "hybrid": MODE_HYBRID}[mode]))
+        self._h = h
+        self._out = torch.empty((cap, codec.k, codec.S), dtype=torch.uint8, device=codec.device)
+        self._fail = torch.empty((cap,), dtype=torch.uint8, device=codec.device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.ldpc_rx_stream_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _collect(self, nd, blocks):
+        torch.cuda.synchronize()
+        return [(int(blocks[i]), self._out[i].clone(), int(self._fail[i].item())) for i in range(nd)]
+
+    def push(self, packets: torch.Tensor, len8: torch.Tensor | None = None):
+        c = self.codec
+        assert packets.is_cuda and packets.dtype == torch.uint8 and packets.is_contiguous() and packets.shape[1] == 8 + c.S
+        blocks = (C.c_int32 * self.cap)()
+        nd = C.c_int(0)
+        _lib.check(self.lib.ldpc_rx_stream_push(self._h, _ptr(packets), _ptr(len8), packets.shape[0], _ptr(self._out), _ptr(self._fail),
+                                                blocks, self.cap, C.byref(nd), _stream()))
+        return self._collect(nd.value, blocks)
+
+    def flush(self):
+        blocks = (C.c_int32 * self.cap)()
+        nd = C.c_int(0)
+        _lib.check(self.lib.ldpc_rx_stream_flush(self._h, _ptr(self._out), _ptr(self._fail), blocks, self.cap, C.byref(nd), _stream()))
+        return self._collect(nd.value, blocks)
+
+    def state(self):
+        st = (C.c_int32 * 4)()
+        _lib.check(self.lib.ldpc_rx_stream_state(self._h, C.byref(st)))
+        return dict(cur=st[0], next=st[1], cur_cnt=st[2], next_cnt=st[3])
 
 
 class NbLdpcCodec:

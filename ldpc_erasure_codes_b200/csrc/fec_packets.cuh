@@ -8,6 +8,9 @@
 // buffers {current, next}; here a whole window of B <= 256 blocks (block numbers are modulo 256) is assembled at
 // once: every packet is independent, so it is a scatter -- one sub-warp per packet, 8-byte accesses because
 // packets are 8 + S bytes apart.  Both kernels are HBM bound (copy with a header): 2 * (8 + S) bytes per packet.
+// Variable payload length (sender :162 `num_longs_used = ceil((packetLen - 2) / 2)`, :186-197; receiver :94-111 reads that
+// many 8-byte words): a packet still occupies an 8 + S byte slot, `len8[packet]` says how many payload words are
+// valid; the sender zero-fills the rest of the slot, the receiver leaves the rest of the symbol zero.
 #pragma once
 #include <cstdint>
 
@@ -24,15 +27,17 @@ __host__ __device__ inline unsigned long long fec_header(uint32_t block, uint32_
 // cw [B][n][S] -> packets [B*n][8+S]; LPP lanes per packet (a power of two <= 32)
 template <int LPP>
 __global__ void __launch_bounds__(256) packetize_kernel(const unsigned long long *__restrict__ cw, unsigned long long *__restrict__ packets,
-                                                        long long n_packets, int n, int words /* S/8 */, uint32_t block0)
+                                                        long long n_packets, int n, int words /* S/8 */, uint32_t block0,
+                                                        const uint16_t *__restrict__ len8 /* or nullptr */)
 {
     const int sub = threadIdx.x % LPP;
     for (long long pk = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / LPP; pk < n_packets;
          pk += (long long)gridDim.x * blockDim.x / LPP) {
         const unsigned long long *src = cw + pk * words;
         unsigned long long *dst = packets + pk * (words + 1);
+        const int used = len8 ? min(int(len8[pk]), words) : words;
         if (sub == 0) dst[0] = fec_header(block0 + uint32_t(pk / n), uint32_t(pk % n));
-        for (int w = sub; w < words; w += LPP) dst[1 + w] = src[w];
+        for (int w = sub; w < words; w += LPP) dst[1 + w] = w < used ? src[w] : 0ull;
     }
 }
 
@@ -53,7 +58,8 @@ __global__ void __launch_bounds__(256) fec_mask_init_kernel(uint32_t *mask, long
 template <int LPP>
 __global__ void __launch_bounds__(256) depacketize_kernel(const unsigned long long *__restrict__ packets, long long n_packets,
                                                           unsigned long long *__restrict__ cw, uint32_t *mask, uint32_t *counts,
-                                                          long long B, int n, int NW, int words, uint32_t block0)
+                                                          long long B, int n, int NW, int words, uint32_t block0,
+                                                          const uint16_t *__restrict__ len8 /* or nullptr */)
 {
     __shared__ unsigned int hist[257];            // per-block packet counts of this CTA ([256] = dropped)
     for (int i = threadIdx.x; i < 257; i += blockDim.x) hist[i] = 0u;
@@ -71,7 +77,8 @@ __global__ void __launch_bounds__(256) depacketize_kernel(const unsigned long lo
             continue;
         }
         unsigned long long *dst = cw + ((long long)rel * n + sym) * words;
-        for (int w = sub; w < words; w += LPP) dst[w] = src[1 + w];
+        const int used = len8 ? min(int(len8[pk]), words) : words;
+        for (int w = sub; w < used; w += LPP) dst[w] = src[1 + w];
         if (sub == 0) {
             atomicAnd(&mask[(long long)rel * NW + (sym >> 5)], ~(1u << (sym & 31)));
             atomicAdd(&hist[rel], 1u);

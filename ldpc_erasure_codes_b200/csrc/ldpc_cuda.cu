@@ -716,7 +716,7 @@ extern "C" int ldpc_fill_random(void *d_dst, int64_t nbytes, uint32_t seed, uint
 // ------------------------------------------------------------------------------------------
 // FEC packet front-ends
 // ------------------------------------------------------------------------------------------
-extern "C" int ldpc_packetize(ldpc_ctx *c, const void *d_cw, uint32_t block0, int64_t B, void *d_packets, void *stream)
+static int packetize_impl(ldpc_ctx *c, const void *d_cw, const uint16_t *d_len8, uint32_t block0, int64_t B, void *d_packets, void *stream)
 {
     if (!c || B < 0) return fail(LDPC_ERR_ARG, "bad argument to ldpc_packetize");
     if (B == 0) return LDPC_OK;
@@ -730,7 +730,7 @@ extern "C" int ldpc_packetize(ldpc_ctx *c, const void *d_cw, uint32_t block0, in
     ProfScope ps(c, LDPC_K_CHANNEL, st);
     auto go = [&](auto kern) {
         kern<<<grid, 256, 0, st>>>(static_cast<const unsigned long long *>(d_cw), static_cast<unsigned long long *>(d_packets), np, c->code.n,
-                                   words, block0);
+                                   words, block0, d_len8);
     };
     if (lpp == 32) go(packetize_kernel<32>);
     else if (lpp == 8) go(packetize_kernel<8>);
@@ -740,8 +740,21 @@ extern "C" int ldpc_packetize(ldpc_ctx *c, const void *d_cw, uint32_t block0, in
     return LDPC_OK;
 }
 
-extern "C" int ldpc_depacketize(ldpc_ctx *c, const void *d_packets, int64_t n_packets, uint32_t block0, int64_t B,
-                                void *d_cw, uint32_t *d_mask, uint32_t *d_counts, void *stream)
+extern "C" int ldpc_packetize(ldpc_ctx *c, const void *d_cw, uint32_t block0, int64_t B, void *d_packets, void *stream)
+{
+    return packetize_impl(c, d_cw, nullptr, block0, B, d_packets, stream);
+}
+
+extern "C" int ldpc_packetize_var(ldpc_ctx *c, const void *d_cw, const uint16_t *d_len8, uint32_t block0, int64_t B, void *d_packets,
+                                  void *stream)
+{
+    if (!d_len8) return fail(LDPC_ERR_ARG, "ldpc_packetize_var: d_len8 is NULL");
+    return packetize_impl(c, d_cw, d_len8, block0, B, d_packets, stream);
+}
+
+// append = the block buffers already hold a partly assembled window: no zero fill, masks and counts keep their state
+static int depacketize_impl(ldpc_ctx *c, const void *d_packets, const uint16_t *d_len8, int64_t n_packets, uint32_t block0, int64_t B,
+                            void *d_cw, uint32_t *d_mask, uint32_t *d_counts, bool append, void *stream)
 {
     if (!c || B < 0 || n_packets < 0) return fail(LDPC_ERR_ARG, "bad argument to ldpc_depacketize");
     if (B > 256) return fail(LDPC_ERR_ARG, "ldpc_depacketize: block numbers are modulo 256, a window holds at most 256 blocks");
@@ -750,20 +763,20 @@ extern "C" int ldpc_depacketize(ldpc_ctx *c, const void *d_packets, int64_t n_pa
     CUDA_TRY(cudaSetDevice(c->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int words = c->S / 8;
-    CUDA_TRY(cudaMemsetAsync(d_cw, 0, size_t(B) * c->code.n * c->S, st));       // missing symbols are all-zero (receiver :59-68)
-    {
+    if (!append) {
+        CUDA_TRY(cudaMemsetAsync(d_cw, 0, size_t(B) * c->code.n * c->S, st));       // missing symbols are all-zero (receiver :59-68)
         ProfScope ps(c, LDPC_K_CHANNEL, st);
         const int grid = int(std::min<long long>((B * c->NW + 255) / 256, (long long)c->num_sms * 8));
         fec_mask_init_kernel<<<grid, 256, 0, st>>>(d_mask, B, c->code.n, c->NW, d_counts);
+        CUDA_TRY(cudaGetLastError());
     }
-    CUDA_TRY(cudaGetLastError());
     if (n_packets > 0) {
         ProfScope ps(c, LDPC_K_CHANNEL, st);
         const int lpp = words >= 32 ? 32 : (words >= 8 ? 8 : (words >= 4 ? 4 : 2));
         const int grid = int(std::min<long long>((n_packets * lpp + 255) / 256, (long long)c->num_sms * 32));
         auto args = [&](auto kern) {
             kern<<<grid, 256, 0, st>>>(static_cast<const unsigned long long *>(d_packets), n_packets, static_cast<unsigned long long *>(d_cw),
-                                       d_mask, d_counts, B, c->code.n, c->NW, words, block0);
+                                       d_mask, d_counts, B, c->code.n, c->NW, words, block0, d_len8);
         };
         if (lpp == 32) args(depacketize_kernel<32>);
         else if (lpp == 8) args(depacketize_kernel<8>);
@@ -774,12 +787,168 @@ extern "C" int ldpc_depacketize(ldpc_ctx *c, const void *d_packets, int64_t n_pa
     return debug_sync("depacketize_kernel", st);
 }
 
+extern "C" int ldpc_depacketize(ldpc_ctx *c, const void *d_packets, int64_t n_packets, uint32_t block0, int64_t B,
+                                void *d_cw, uint32_t *d_mask, uint32_t *d_counts, void *stream)
+{
+    return depacketize_impl(c, d_packets, nullptr, n_packets, block0, B, d_cw, d_mask, d_counts, false, stream);
+}
+
+extern "C" int ldpc_depacketize_var(ldpc_ctx *c, const void *d_packets, const uint16_t *d_len8, int64_t n_packets, uint32_t block0, int64_t B,
+                                    void *d_cw, uint32_t *d_mask, uint32_t *d_counts, void *stream)
+{
+    if (n_packets > 0 && !d_len8) return fail(LDPC_ERR_ARG, "ldpc_depacketize_var: d_len8 is NULL");
+    return depacketize_impl(c, d_packets, d_len8, n_packets, block0, B, d_cw, d_mask, d_counts, false, stream);
+}
+
 extern "C" int ldpc_ready_to_decode(const ldpc_ctx *c, int cur_block_cnt, int next_block_cnt)
 {
     if (!c) return 0;
     const int n = c->code.n, k = c->code.k, m = n - k;
     const int desired = int(double(m) * 0.8 + 0.5), minimum = int(double(m) * 0.2 + 0.5);
     return (cur_block_cnt == n) || (cur_block_cnt > k + desired && next_block_cnt > 10) || (cur_block_cnt > k + minimum && next_block_cnt > 100);
+}
+
+// ------------------------------------------------------------------------------------------
+// receiver with two block buffers (the rest of it): the streaming state machine of
+// OpenCL/device/ldpc_erasure_decoder_with_reordering_logic.cl:45-142 -- two block buffers {current, next}, packets
+// of other blocks dropped (:105,124), arrival counters (:112-131), the hand-off rule evaluated after every packet
+// (:139) -- as a host object over the packet kernel and the decoder.  The headers of a pushed batch are read back,
+// the per-packet control runs on the host exactly as the reference's loop does, and the payload goes block by block
+// through depacketize (appending to the window) and ldpc_decode on the GPU.  What the committed sketch leaves open
+// (it stops compiling after the rule) is completed in the obvious way: the decoded block is emitted, `next` becomes
+// `current` (block numbers modulo 256), its counter is kept, and the freed buffer is cleared for the new `next`.
+// ------------------------------------------------------------------------------------------
+struct ldpc_rx_stream {
+    ldpc_ctx *c = nullptr;
+    int max_iter = 50, mode = LDPC_MODE_PEEL;
+    int cur = -1, next = -1;
+    long long cur_cnt = 0, next_cnt = 0;
+    uint8_t *d_win = nullptr;       // [2][n][S]
+    uint32_t *d_mask = nullptr;     // [2][NW]
+    uint32_t *d_counts = nullptr;   // [3]
+    std::vector<unsigned long long> hdr;
+};
+
+extern "C" int ldpc_decode_ex(ldpc_ctx *c, const void *d_cw, const uint32_t *d_mask, void *d_out, uint8_t *d_fail,
+                              uint8_t *d_fail_any, int max_iter, int mode, int64_t B, void *stream);
+
+extern "C" int ldpc_rx_stream_create(ldpc_rx_stream **out, ldpc_ctx *c, int max_iter, int mode)
+{
+    if (!out || !c) return fail(LDPC_ERR_ARG, "NULL argument to ldpc_rx_stream_create");
+    *out = nullptr;
+    if (mode != LDPC_MODE_PEEL && mode != LDPC_MODE_HYBRID) return fail(LDPC_ERR_ARG, "unknown decode mode");
+    ldpc_rx_stream *s = new (std::nothrow) ldpc_rx_stream();
+    if (!s) return fail(LDPC_ERR_NOMEM, "out of host memory");
+    s->c = c; s->max_iter = max_iter; s->mode = mode;
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaError_t e = cudaMalloc(&s->d_win, size_t(2) * c->code.n * c->S);
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_mask, size_t(2) * c->NW * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_counts, 3 * 4);
+    if (e != cudaSuccess) {
+        cudaFree(s->d_win); cudaFree(s->d_mask); cudaFree(s->d_counts);
+        delete s;
+        return fail(LDPC_ERR_NOMEM, std::string("ldpc_rx_stream_create: ") + cudaGetErrorString(e));
+    }
+    *out = s;
+    return LDPC_OK;
+}
+
+extern "C" int ldpc_rx_stream_destroy(ldpc_rx_stream *s)
+{
+    if (!s) return LDPC_OK;
+    cudaSetDevice(s->c->device);
+    cudaFree(s->d_win); cudaFree(s->d_mask); cudaFree(s->d_counts);
+    delete s;
+    return LDPC_OK;
+}
+
+extern "C" int ldpc_rx_stream_state(const ldpc_rx_stream *s, int32_t state[4])
+{
+    if (!s || !state) return fail(LDPC_ERR_ARG, "NULL argument");
+    state[0] = s->cur; state[1] = s->next; state[2] = int32_t(s->cur_cnt); state[3] = int32_t(s->next_cnt);
+    return LDPC_OK;
+}
+
+// decode the current block as it stands, emit it, make `next` the current block
+static int rx_stream_hand_off(ldpc_rx_stream *s, void *d_out, uint8_t *d_fail, int32_t *h_blocks, int cap, int *n_dec, cudaStream_t st)
+{
+    ldpc_ctx *c = s->c;
+    if (*n_dec >= cap) return fail(LDPC_ERR_ARG, "ldpc_rx_stream: more blocks became ready than the output holds (cap)");
+    const size_t blk = size_t(c->code.n) * c->S, outb = size_t(c->code.k) * c->S;
+    int rc = ldpc_decode_ex(c, s->d_win, s->d_mask, static_cast<uint8_t *>(d_out) + size_t(*n_dec) * outb, d_fail ? d_fail + *n_dec : nullptr,
+                            nullptr, s->max_iter, s->mode, 1, st);
+    if (rc) return rc;
+    if (h_blocks) h_blocks[*n_dec] = s->cur;
+    (*n_dec)++;
+    CUDA_TRY(cudaMemcpyAsync(s->d_win, s->d_win + blk, blk, cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(s->d_mask, s->d_mask + c->NW, size_t(c->NW) * 4, cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(s->d_win + blk, 0, blk, st));
+    fec_mask_init_kernel<<<1, 256, 0, st>>>(s->d_mask + c->NW, 1, c->code.n, c->NW, s->d_counts + 1);
+    CUDA_TRY(cudaGetLastError());
+    s->cur = s->next;
+    s->next = (s->cur + 1) & 0xff;
+    s->cur_cnt = s->next_cnt;
+    s->next_cnt = 0;
+    return LDPC_OK;
+}
+
+extern "C" int ldpc_rx_stream_push(ldpc_rx_stream *s, const void *d_packets, const uint16_t *d_len8, int64_t n_packets, void *d_out,
+                                   uint8_t *d_fail, int32_t *h_blocks, int cap, int *n_decoded, void *stream)
+{
+    if (!s || n_packets < 0 || !n_decoded || (n_packets > 0 && !d_packets) || !d_out) return fail(LDPC_ERR_ARG, "bad argument to ldpc_rx_stream_push");
+    *n_decoded = 0;
+    if (n_packets == 0) return LDPC_OK;
+    ldpc_ctx *c = s->c;
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t ps = 8 + size_t(c->S);
+    s->hdr.resize(size_t(n_packets));
+    CUDA_TRY(cudaMemcpy2DAsync(s->hdr.data(), 8, d_packets, ps, 8, size_t(n_packets), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    const uint8_t *pk = static_cast<const uint8_t *>(d_packets);
+    int64_t seg0 = 0;
+    auto place = [&](int64_t upto) -> int {      // packets [seg0, upto) into the window {cur, next}
+        if (upto <= seg0 || s->cur < 0) { seg0 = upto; return LDPC_OK; }
+        int rc = depacketize_impl(c, pk + size_t(seg0) * ps, d_len8 ? d_len8 + seg0 : nullptr, upto - seg0, uint32_t(s->cur), 2, s->d_win, s->d_mask,
+                                  s->d_counts, true, st);
+        seg0 = upto;
+        return rc;
+    };
+    for (int64_t i = 0; i < n_packets; i++) {
+        const unsigned long long h = s->hdr[size_t(i)];
+        const uint32_t lo = uint32_t(h), hi = uint32_t(h >> 32);
+        const bool valid = lo == hi && ((lo >> 24) & 0xffu) == kFecClass && int(lo & 0xffffu) < c->code.n;
+        const int blk = int((lo >> 16) & 0xffu);
+        if (s->cur < 0) {                       // the first packet names the current block (:88-91); an unusable header does not
+            if (!valid) continue;
+            s->cur = blk; s->next = (blk + 1) & 0xff;
+            seg0 = i;
+            CUDA_TRY(cudaMemsetAsync(s->d_win, 0, size_t(2) * c->code.n * c->S, st));
+            fec_mask_init_kernel<<<1, 256, 0, st>>>(s->d_mask, 2, c->code.n, c->NW, s->d_counts);
+            CUDA_TRY(cudaGetLastError());
+        }
+        if (valid && blk == s->cur) s->cur_cnt++;
+        else if (valid && blk == s->next) s->next_cnt++;
+        if (ldpc_ready_to_decode(c, int(s->cur_cnt), int(s->next_cnt))) {      // (:139), after every packet
+            int rc = place(i + 1);
+            if (!rc) rc = rx_stream_hand_off(s, d_out, d_fail, h_blocks, cap, n_decoded, st);
+            if (rc) return rc;
+        }
+    }
+    return place(n_packets);
+}
+
+extern "C" int ldpc_rx_stream_flush(ldpc_rx_stream *s, void *d_out, uint8_t *d_fail, int32_t *h_blocks, int cap, int *n_decoded, void *stream)
+{
+    if (!s || !n_decoded || !d_out) return fail(LDPC_ERR_ARG, "bad argument to ldpc_rx_stream_flush");
+    *n_decoded = 0;
+    CUDA_TRY(cudaSetDevice(s->c->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    for (int round = 0; round < 2 && s->cur >= 0 && s->cur_cnt > 0; round++) {
+        int rc = rx_stream_hand_off(s, d_out, d_fail, h_blocks, cap, n_decoded, st);
+        if (rc) return rc;
+    }
+    return LDPC_OK;
 }
 
 // ------------------------------------------------------------------------------------------

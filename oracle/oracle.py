@@ -262,3 +262,61 @@ def nb_decode(code: Code, coef: np.ndarray, payload: np.ndarray, erased: np.ndar
                               C.c_int(S), C.c_int64(B), _p(payload), _p(erased), _p(out), _p(fail), _p(iters), _p(status),
                               C.c_int(max_iter), C.c_int({"peel": 0, "hybrid": 1}[mode]), C.c_int(nthreads))
     return dict(out=out, payload=payload, erased=erased, fail_sys=fail, iters=iters, status=status)
+
+
+# ---- variable payload length and the receiver's two-buffer state machine (the rest) ----------------
+def packetize_var(cw: np.ndarray, len8: np.ndarray, block0: int) -> np.ndarray:
+    """Sender with num_longs_used (encoder_VITA_in_UDP_out.cl:162,186-197): header, len8 payload words, zeros."""
+    pk = packetize(cw, block0)
+    for i, l in enumerate(np.asarray(len8).reshape(-1)):
+        pk[i, 8 + 8 * int(l):] = 0
+    return pk
+
+
+def rx_stream(code: Code, packets: np.ndarray, len8=None, max_iter=50, mode="peel", flush=True):
+    """The per-packet loop of ldpc_erasure_decoder_with_reordering_logic.cl:71-142, one packet at a time in plain Python:
+    two block buffers {current, next} (:45-50), the first usable packet names the current block (:88-91; next = current + 1
+    modulo 256), a packet of any other block is dropped (:105,124), its payload words are placed and its flag cleared
+    (:94-131), and after every packet the hand-off rule (:139).  On hand-off the current block is decoded as it stands and
+    emitted; next becomes current, keeps its counter, and the freed buffer is cleared.  Returns [(block, out [k][S], fail)]."""
+    n, k = code.n, code.k
+    S = packets.shape[1] - 8
+    buf = np.zeros((2, n, S), dtype=np.uint8)
+    er = np.ones((2, n), dtype=np.uint8)
+    cur, nxt, cur_cnt, nxt_cnt = -1, -1, 0, 0
+    out = []
+
+    def hand_off():
+        nonlocal cur, nxt, cur_cnt, nxt_cnt
+        d = decode(code, buf[0:1], er[0:1], max_iter=max_iter, mode=mode)
+        out.append((cur, d["out"][0], int(d["fail_sys"][0])))
+        buf[0], er[0] = buf[1], er[1]
+        buf[1], er[1] = 0, 1
+        cur, nxt = nxt, (nxt + 1) & 0xFF
+        cur_cnt, nxt_cnt = nxt_cnt, 0
+
+    for i in range(packets.shape[0]):
+        h = int(np.frombuffer(packets[i, :8].tobytes(), dtype=np.uint64)[0])
+        lo, hi = h & 0xFFFFFFFF, h >> 32
+        cls, blk, sym = (lo >> 24) & 0xFF, (lo >> 16) & 0xFF, lo & 0xFFFF
+        valid = lo == hi and cls == 1 and sym < n
+        if cur < 0:
+            if not valid:
+                continue
+            cur, nxt = blk, (blk + 1) & 0xFF
+        used = S if len8 is None else 8 * int(len8[i])
+        if valid and blk == cur:
+            buf[0, sym, :used] = packets[i, 8:8 + used]
+            er[0, sym] = 0
+            cur_cnt += 1
+        elif valid and blk == nxt:
+            buf[1, sym, :used] = packets[i, 8:8 + used]
+            er[1, sym] = 0
+            nxt_cnt += 1
+        if ready_to_decode(n, k, cur_cnt, nxt_cnt):
+            hand_off()
+    if flush:
+        for _ in range(2):
+            if cur >= 0 and cur_cnt > 0:
+                hand_off()
+    return out

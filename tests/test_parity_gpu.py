@@ -811,3 +811,92 @@ def test_decode_host_multi_fans_out(codecs):
         decode_host_multi([cs[0], cs[0]], h_rx, h_mask)            # a context listed twice
     for c in cs:
         c.close()
+
+
+# ---- SURVEY 8(f) rank 1, the rest: variable payload length, two-buffer receiver -------------------------------------------
+def test_variable_payload_length_packets(codecs):
+    """num_longs_used (encoder_VITA_in_UDP_out.cl:162,186-197; receiver :94-111): per-packet payload length."""
+    import torch
+    from ldpc_erasure_codes_b200.codec import unpack_mask
+    codec = codecs(1, 64)
+    code = orc.Code.builtin(1)
+    B = 3
+    cw = codec.encode(_rand_info(B, codec.k, 64, seed=21))
+    rng = np.random.default_rng(4)
+    len8 = rng.integers(0, 9, B * codec.n).astype(np.int16)
+    d_len = torch.from_numpy(len8).cuda()
+    pk = codec.packetize(cw, block0=254, len8=d_len)
+    assert np.array_equal(_np(pk), orc.packetize_var(_np(cw), len8, 254))
+    keep = rng.permutation(pk.shape[0])[: int(0.9 * pk.shape[0])]
+    sel = torch.from_numpy(keep).cuda()
+    noisy = pk[sel].clone()
+    cw2, mask2, counts = codec.depacketize(noisy.contiguous(), 254, B, len8=d_len[sel].contiguous())
+    ref = np.zeros((B, codec.n, 64), np.uint8)
+    flags = np.ones((B, codec.n), np.uint8)
+    h_pk = _np(noisy)
+    for i, src in enumerate(keep):
+        b, sym = divmod(int(src), codec.n)
+        ref[b, sym, : 8 * len8[src]] = h_pk[i, 8: 8 + 8 * len8[src]]
+        flags[b, sym] = 0
+    assert np.array_equal(_np(cw2), ref) and np.array_equal(unpack_mask(mask2, codec.n), flags)
+    # garbage behind the valid words of a slot must not reach the symbol
+    junk = pk[sel].clone()
+    junk[:, 8 + 16:] = 0xAB
+    short = torch.full((len(keep),), 2, dtype=torch.int16, device="cuda")
+    cw3, _, _ = codec.depacketize(junk.contiguous(), 254, B, len8=short)
+    assert int(_np(cw3)[:, :, 16:].max()) == 0
+
+
+@pytest.mark.parametrize("mode,it,loss", [("peel", 50, 0.08), ("hybrid", 10, 0.17)])
+def test_rx_stream_two_buffer_state_machine(codecs, mode, it, loss):
+    """ldpc_erasure_decoder_with_reordering_logic.cl:45-142 against its plain-Python restatement: five blocks whose numbers
+    wrap past 255, packets of neighbouring blocks interleaved, losses, duplicates, a foreign block, pushed in ragged batches."""
+    import torch
+    from ldpc_erasure_codes_b200.codec import RxStream
+    codec = codecs(1, 64)
+    code = orc.Code.builtin(1)
+    NB, block0 = 5, 253
+    info = _rand_info(NB, codec.k, 64, seed=77)
+    cw = codec.encode(info)
+    pk = _np(codec.packetize(cw, block0=block0))
+    rng = np.random.default_rng(5)
+    order = []
+    for b in range(NB):                       # block b's packets, the tail of each block mixed with the head of the next
+        idx = b * codec.n + rng.permutation(codec.n)
+        idx = idx[rng.random(codec.n) >= loss]
+        order.append(idx)
+    stream = []
+    for b in range(NB):
+        head, tail = order[b][:-300], order[b][-300:]
+        stream.extend(head.tolist())
+        nxt_head = order[b + 1][:200].tolist() if b + 1 < NB else []
+        mix = tail.tolist() + nxt_head
+        rng.shuffle(mix)
+        stream.extend(mix)
+        if b + 1 < NB:
+            order[b + 1] = order[b + 1][200:]
+    stream = np.array(stream)
+    arr = pk[stream]
+    arr = np.concatenate([arr[:500], arr[100:130], arr[500:]])                 # duplicates
+    foreign = pk[:40].copy()
+    foreign[:, 2] = foreign[:, 6] = (block0 + 77) & 0xFF                        # a block outside the window
+    arr = np.concatenate([arr[:900], foreign, arr[900:]])
+    ref = orc.rx_stream(code, arr, max_iter=it, mode=mode)
+    rx = RxStream(codec, max_iter=it, mode=mode, cap=4)
+    got = []
+    d_arr = torch.from_numpy(arr).cuda()
+    pos = 0
+    while pos < len(arr):
+        step = int(rng.integers(1, 1500))
+        got += rx.push(d_arr[pos:pos + step].contiguous())
+        pos += step
+    got += rx.flush()
+    rx.close()
+    assert [g[0] for g in got] == [r[0] for r in ref] and len(ref) >= NB
+    for g, r in zip(got, ref):
+        assert g[2] == r[2] and np.array_equal(_np(g[1]), r[1])
+    decoded = {g[0]: _np(g[1]) for g in got if g[2] == 0}
+    assert len(decoded) >= NB - 1
+    for b in range(NB):
+        if (block0 + b) & 0xFF in decoded:
+            assert np.array_equal(decoded[(block0 + b) & 0xFF], _np(info)[b])
