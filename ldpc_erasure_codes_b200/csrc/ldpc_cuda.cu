@@ -1388,7 +1388,7 @@ struct ldpc_nb_ctx {
     uint8_t *d_work = nullptr;              // [work_batch][n][S]
     unsigned int *d_list = nullptr, *d_count = nullptr;
     uint8_t *d_gA = nullptr, *d_gB = nullptr;
-    int ge_grid = 0, ge_smem = 0;
+    int ge_grid = 0, ge_smem = 0, ge_small = 0;
 };
 
 static void nb_free(ldpc_nb_ctx *c)
@@ -1514,7 +1514,8 @@ extern "C" int ldpc_nb_decode(ldpc_nb_ctx *c, const void *d_cw, const uint32_t *
         if (!c->d_work) {      // first hybrid call: the work buffer (whole codewords after the sweeps) and the elimination workspaces
             c->work_batch = std::max<long long>(1, std::min<long long>(b->max_batch, (1ll << 30) / (long long)in_cw));
             c->ge_grid = b->num_sms;
-            c->ge_smem = 768 + b->NW * 4 + ((b->NW + 1) & ~1) * 2 + ((b->code.m + 3) & ~3) + 3 * b->code.m * 2 + 64;
+            c->ge_small = 768 + b->NW * 4 + ((b->NW + 1) & ~1) * 2 + ((b->code.m + 3) & ~3) + 3 * b->code.m * 2 + 64;
+            c->ge_smem = b->smem_optin - 1024;       // the rest is the work area: A and b of a residual set that fits
             cudaError_t e = cudaSuccess;
             auto ok = [&](cudaError_t r) { if (e == cudaSuccess) e = r; return e == cudaSuccess; };
             if (!(ok(cudaMalloc(&c->d_work, size_t(c->work_batch) * in_cw)) && ok(cudaMalloc(&c->d_gA, size_t(c->ge_grid) * b->code.m * b->code.m)) &&
@@ -1560,6 +1561,8 @@ extern "C" int ldpc_nb_decode(ldpc_nb_ctx *c, const void *d_cw, const uint32_t *
             gp.work = c->d_work; gp.mask = mask; gp.sched = b->d_sched; gp.list = c->d_list; gp.list_count = c->d_count; gp.fail = failp;
             gp.stats = b->d_stats; gp.cidx = b->d_cidx; gp.coef = c->d_coef; gp.tab = c->d_tab; gp.gA = c->d_gA; gp.gB = c->d_gB;
             gp.n = b->code.n; gp.k = b->code.k; gp.m = b->code.m; gp.RW = b->code.RW; gp.NW = b->NW; gp.S = b->S; gp.stride = b->sched_stride;
+            gp.work_bytes = c->ge_smem - c->ge_small;
+            { int rcs = allow_max_smem(reinterpret_cast<const void *>(nb_ge_kernel), b->smem_optin); if (rcs) return rcs; }
             {
                 ProfScope ps(b, LDPC_K_HYBRID_CTA, st);
                 nb_ge_kernel<<<c->ge_grid, kNbThreads, c->ge_smem, st>>>(gp);

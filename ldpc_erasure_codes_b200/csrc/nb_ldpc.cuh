@@ -19,8 +19,9 @@
 //     bit planes, acc_j ^= x_u & mask_j(g_u) (one LOP3 per plane and word; the masks of every constant sit in shared
 //     memory), and folds the planes once per entry by Horner's rule, r = (...(acc_7 * 2 ^ acc_6) * 2 ...) ^ acc_0
 //     (seven doublings of five ALU operations) -- 8 operations per member and word instead of ~48.
-//   nb_ge_kernel  one CTA per codeword that still has erasures: A = H(:, E) (dense bytes, in an L2-resident per-CTA
-//     workspace), b = sum_{known} h * y, Gauss-Jordan with the lowest unused row as pivot.  The MATLAB code aborts
+//   nb_ge_kernel  one CTA per codeword that still has erasures: A = H(:, E) (dense bytes: in shared memory when the
+//     residual set fits, else in an L2-resident per-CTA workspace), b = sum_{known} h * y, Gauss-Jordan with the lowest
+//     unused row as pivot.  The MATLAB code aborts
 //     iff a column has no pivot, i.e. iff rank(A) < |E|; otherwise the solution is unique and any exact solver
 //     returns its bytes.  On abort the state after the sweeps is kept and the frame reported, as for the binary
 //     hybrid decoder.
@@ -135,12 +136,14 @@ struct NbGeParams {
     const uint16_t *cidx;       // [m][RW]
     const uint8_t *coef;        // [m][RW]
     const uint8_t *tab;         // log | alog
-    uint8_t *gA;                // [grid][m][m] workspace: A
-    uint8_t *gB;                // [grid][m][S] workspace: right-hand sides
+    uint8_t *gA;                // [grid][m][m] workspace: A, for residual sets too large for shared memory
+    uint8_t *gB;                // [grid][m][S] workspace: right-hand sides, likewise
     int n, k, m, RW, NW, S, stride;
+    int work_bytes;             // shared bytes behind the small arrays: A (and b) live there when they fit
 };
 
-// shared: log/alog 768 | unknown bitmap [NW] u32 | prefix [NW] u16 | used [m] u8 | piv [m] u16 | rows list [m] u16 | E [m] u16
+// shared: log/alog 768 | unknown bitmap [NW] u32 | prefix [NW] u16 | used [m] u8 | piv [m] u16 | rows list [m] u16 | E [m] u16 |
+//         work area: A [m][lda] and b [m][S] when they fit (a residual set of ~250 symbols: 510 x 256 + 510 x 64 bytes)
 __global__ void __launch_bounds__(kNbThreads) nb_ge_kernel(const NbGeParams p)
 {
     extern __shared__ __align__(16) uint8_t gsm[];
@@ -152,11 +155,10 @@ __global__ void __launch_bounds__(kNbThreads) nb_ge_kernel(const NbGeParams p)
     uint16_t *piv = reinterpret_cast<uint16_t *>(used + ((p.m + 3) & ~3));
     uint16_t *rlist = piv + p.m;
     uint16_t *Evar = rlist + p.m;
+    uint8_t *work_s = reinterpret_cast<uint8_t *>(Evar + p.m) + ((16 - (reinterpret_cast<uintptr_t>(Evar + p.m) & 15)) & 15);
     __shared__ int s_e, s_piv, s_nrows, s_abort;
     const int tid = threadIdx.x, m = p.m, S = p.S;
     for (int i = tid; i < 768; i += kNbThreads) lg[i] = p.tab[i];
-    uint8_t *A = p.gA + size_t(blockIdx.x) * m * m;
-    uint8_t *Bv = p.gB + size_t(blockIdx.x) * m * S;
     auto mul = [&](uint32_t a, uint32_t b) -> uint32_t { return (a && b) ? al[int(lg[a]) + int(lg[b])] : 0u; };
     __syncthreads();
 
@@ -192,13 +194,20 @@ __global__ void __launch_bounds__(kNbThreads) nb_ge_kernel(const NbGeParams p)
             __syncthreads();
             continue;
         }
+        // A and b: in shared memory when this residual set fits, else in the CTA's global workspace (row stride lda)
+        const int lda_s = (e + 15) & ~15;
+        const bool a_sh = m * lda_s <= p.work_bytes - 16;
+        const bool b_sh = a_sh && m * lda_s + m * S <= p.work_bytes - 16;
+        const int lda = a_sh ? lda_s : m;
+        uint8_t *A = a_sh ? work_s : p.gA + size_t(blockIdx.x) * m * m;
+        uint8_t *Bv = b_sh ? work_s + size_t(m) * lda_s : p.gB + size_t(blockIdx.x) * m * S;
         for (int w = tid; w < p.NW; w += kNbThreads) {
             uint32_t x = unk[w];
             int at = pre[w];
             while (x) { const int bit = __ffs(x) - 1; x &= x - 1; Evar[at++] = uint16_t(w * 32 + bit); }
         }
         // ---- A = H(:, E), b = sum over the known members h * y ------------------------------------------
-        for (int i = tid; i < m * e; i += kNbThreads) A[size_t(i / e) * m + (i % e)] = 0;
+        for (int i = tid; i < m * e; i += kNbThreads) A[size_t(i / e) * lda + (i % e)] = 0;
         for (int i = tid; i < m; i += kNbThreads) used[i] = 0;
         __syncthreads();
         for (int r = tid / 32; r < m; r += kNbThreads / 32) {             // a warp per check row
@@ -219,7 +228,7 @@ __global__ void __launch_bounds__(kNbThreads) nb_ge_kernel(const NbGeParams p)
             if ((tid & 31) < p.RW) {
                 const uint32_t u = row[tid & 31];
                 if (u != 0xFFFFu && ((unk[u >> 5] >> (u & 31)) & 1u))
-                    A[size_t(r) * m + pre[u >> 5] + __popc(unk[u >> 5] & ((1u << (u & 31)) - 1u))] = hc[tid & 31];
+                    A[size_t(r) * lda + pre[u >> 5] + __popc(unk[u >> 5] & ((1u << (u & 31)) - 1u))] = hc[tid & 31];
             }
         }
         __syncthreads();
@@ -228,25 +237,25 @@ __global__ void __launch_bounds__(kNbThreads) nb_ge_kernel(const NbGeParams p)
             if (tid == 0) { s_piv = m; s_nrows = 0; }
             __syncthreads();
             for (int r = tid; r < m; r += kNbThreads)
-                if (!used[r] && A[size_t(r) * m + col]) atomicMin(&s_piv, r);
+                if (!used[r] && A[size_t(r) * lda + col]) atomicMin(&s_piv, r);
             __syncthreads();
             const int pr = s_piv;
             if (pr >= m) { if (tid == 0) s_abort = 1; break; }            // rank(A) < e (decoder :82-85)
-            const uint32_t inv = al[255 - int(lg[A[size_t(pr) * m + col]])];
+            const uint32_t inv = al[255 - int(lg[A[size_t(pr) * lda + col]])];
             // the other rows with a nonzero entry in this column
             for (int r = tid; r < m; r += kNbThreads)
-                if (r != pr && A[size_t(r) * m + col]) rlist[atomicAdd(&s_nrows, 1)] = uint16_t(r);
+                if (r != pr && A[size_t(r) * lda + col]) rlist[atomicAdd(&s_nrows, 1)] = uint16_t(r);
             __syncthreads();
             // scale the pivot row (entries left of `col` in an unused row are zero)
-            for (int j = col + tid; j < e; j += kNbThreads) A[size_t(pr) * m + j] = uint8_t(mul(inv, A[size_t(pr) * m + j]));
+            for (int j = col + tid; j < e; j += kNbThreads) A[size_t(pr) * lda + j] = uint8_t(mul(inv, A[size_t(pr) * lda + j]));
             for (int b0 = tid; b0 < S; b0 += kNbThreads) Bv[size_t(pr) * S + b0] = uint8_t(mul(inv, Bv[size_t(pr) * S + b0]));
             __syncthreads();
             const int nrows = s_nrows;
             for (int q = tid / 32; q < nrows; q += kNbThreads / 32) {      // a warp per row to clear
                 const int r = rlist[q];
-                const uint32_t f = A[size_t(r) * m + col];
+                const uint32_t f = A[size_t(r) * lda + col];
                 __syncwarp();
-                for (int j = col + (tid & 31); j < e; j += 32) A[size_t(r) * m + j] ^= uint8_t(mul(f, A[size_t(pr) * m + j]));
+                for (int j = col + (tid & 31); j < e; j += 32) A[size_t(r) * lda + j] ^= uint8_t(mul(f, A[size_t(pr) * lda + j]));
                 for (int b0 = tid & 31; b0 < S; b0 += 32) Bv[size_t(r) * S + b0] ^= uint8_t(mul(f, Bv[size_t(pr) * S + b0]));
             }
             if (tid == 0) { used[pr] = 1; piv[col] = uint16_t(pr); }
