@@ -299,27 +299,67 @@ std::vector<uint8_t> make_enc_blob(const HostCode &code, int epw)
 {
     std::vector<uint8_t> blob;
     if (!code.triangular) return blob;
-    const int rows = code.m, nl = code.encode_levels;
-    const std::vector<uint32_t> &entries = code.enc_entries;
-    const std::vector<uint16_t> &lvl_off = code.enc_lvl_off;
-    // passes of the walk over the levels >= 2
-    std::vector<uint16_t> passes;
-    for (int l = 1; l < nl; l++)
-        for (int pos = lvl_off[l]; pos < lvl_off[l + 1]; pos += epw)
-            passes.push_back(uint16_t(pos | ((std::min(epw, lvl_off[l + 1] - pos) - 1) << 11)));
-    // records: the parity members of each row of level >= 2 (its diagonal excluded)
-    const int n1 = nl >= 2 ? int(lvl_off[1]) : rows;
+    const int rows = code.m, k = code.k;
+    // parity members of every row (its diagonal excluded): what the row needs from earlier rows
+    std::vector<std::vector<int>> deps(static_cast<size_t>(rows));
+    for (int r = 0; r < rows; r++)
+        for (int j = code.row_ptr[r]; j < code.row_ptr[r + 1] - 1; j++)
+            if (code.col_idx[j] >= k) deps[size_t(r)].push_back(code.col_idx[j] - k);
+    std::vector<uint32_t> entries;
+    std::vector<uint16_t> lvl_off, passes;
+    int nl = 0, n1 = rows;
+    if (epw <= 0) {
+        // plain level structure (what nb_exec_kernel walks)
+        entries = code.enc_entries;
+        lvl_off = code.enc_lvl_off;
+        nl = code.encode_levels;
+        n1 = nl >= 2 ? int(lvl_off[1]) : rows;
+    } else {
+        // The executor walks PASSES of <= epw mutually independent entries, one after the other (payload_exec.cuh), and a
+        // pass costs the same whether it is full or not.  The levels of this schedule hold ~17-26 entries: cut level by
+        // level they give two passes each, the second nearly empty.  Instead the rows are list-scheduled: a pass takes up
+        // to epw rows whose parity members all lie in earlier passes (or need none), the rows with the longest chain of
+        // dependents first.  Entry order = rows without parity members, then pass by pass (a topological order, which is
+        // all the executor's bulk pass needs); the blob presents them as two "levels".
+        std::vector<int> height(size_t(rows), 1), pass_of(size_t(rows), -2);
+        for (int r = rows - 1; r >= 0; r--)
+            for (int d : deps[size_t(r)]) height[size_t(d)] = std::max(height[size_t(d)], height[size_t(r)] + 1);
+        for (int r = 0; r < rows; r++)
+            if (deps[size_t(r)].empty()) { pass_of[size_t(r)] = -1; entries.push_back(uint32_t(k + r) | (uint32_t(r) << 16)); }
+        n1 = int(entries.size());
+        int left = rows - n1;
+        for (int p = 0; left > 0; p++) {
+            std::vector<int> ready;
+            for (int r = 0; r < rows; r++) {
+                if (pass_of[size_t(r)] != -2) continue;
+                bool ok = true;
+                for (int d : deps[size_t(r)]) if (pass_of[size_t(d)] == -2 || pass_of[size_t(d)] >= p) { ok = false; break; }
+                if (ok) ready.push_back(r);
+            }
+            std::stable_sort(ready.begin(), ready.end(), [&](int a, int b2) { return height[size_t(a)] > height[size_t(b2)]; });
+            const int take = std::min<int>(epw, int(ready.size()));
+            passes.push_back(uint16_t(int(entries.size()) | ((take - 1) << 11)));
+            for (int i = 0; i < take; i++) {
+                pass_of[size_t(ready[size_t(i)])] = p;
+                entries.push_back(uint32_t(k + ready[size_t(i)]) | (uint32_t(ready[size_t(i)]) << 16));
+            }
+            left -= take;
+        }
+        nl = n1 < rows ? 2 : 1;
+        lvl_off.push_back(0);
+        lvl_off.push_back(uint16_t(n1));
+        if (nl == 2) lvl_off.push_back(uint16_t(rows));
+    }
+    // records: the parity members of each walked row
     const int nrec = rows - n1;
     const uint64_t z = uint64_t(sched_zero_row(code.n));
     std::vector<uint64_t> recs(static_cast<size_t>(nrec), 0);
     for (int i = n1; i < n1 + nrec; i++) {
-        const int r = int(entries[i] >> 16);
+        const int r = int(entries[size_t(i)] >> 16);
         uint64_t rec = 0;
         int nd = 0;
-        for (int j = code.row_ptr[r]; j < code.row_ptr[r + 1] - 1; j++) {
-            const int c = code.col_idx[j];
-            if (c < code.k) continue;
-            if (nd < 5) rec |= uint64_t(c) << (12 * nd);
+        for (int d : deps[size_t(r)]) {
+            if (nd < 5) rec |= uint64_t(k + d) << (12 * nd);
             nd++;
         }
         for (int j = nd; j < 5; j++) rec |= z << (12 * j);

@@ -61,7 +61,8 @@ int load_mat_sparse(const std::string &path, const char *var_name, int &rows, in
                     std::vector<int32_t> &col_ptr, std::vector<int32_t> &row_idx, std::string &err);
 int build_code(int rows, int cols, const std::vector<int32_t> &col_ptr,
                const std::vector<int32_t> &row_idx, HostCode &code, std::string &err);
-// The encoder's static schedule as a blob, its walk cut into passes of `epw` entries (empty if H is not triangular).
+// The encoder's static schedule as a blob (empty if H is not triangular): epw > 0 -- for the executor, the rows
+// list-scheduled into passes of <= epw independent entries; epw = 0 -- the plain level structure.
 std::vector<uint8_t> make_enc_blob(const HostCode &code, int epw);
 
 }  // namespace ldpc

@@ -1430,7 +1430,7 @@ extern "C" int ldpc_nb_ctx_create(ldpc_nb_ctx **out, ldpc_ctx *base, const uint8
     rs_host_tables(tab, tab + 256);
     std::vector<uint32_t> m8(256 * 8);
     for (int v = 0; v < 256; v++) for (int j = 0; j < 8; j++) m8[size_t(v * 8 + j)] = ((v >> j) & 1) ? 0xFFFFFFFFu : 0u;
-    const std::vector<uint8_t> blob = make_enc_blob(code, 16);
+    const std::vector<uint8_t> blob = make_enc_blob(code, 0);      // (plain levels: nb_exec_kernel walks them with a CTA barrier each)
     c->enc_blob_bytes = int((blob.size() + 15) & ~size_t(15));
     c->W = base->S % 32 == 0 ? 32 : 16;
     const int fixed = code.m * code.RW * 2 + ((code.m * code.RW + 15) & ~15) + 256 * 8 * 4 + 768;
