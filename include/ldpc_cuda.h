@@ -238,6 +238,21 @@ int ldpc_decode_host_multi(ldpc_ctx *const *ctxs, int n_ctx, const void *h_cw, c
                            void *h_out, uint8_t *h_fail, uint8_t *h_fail_any, int max_iter, int mode,
                            int64_t B);
 
+/* In place (round 2; the reference has no equivalent -- its run() reads the whole output buffer back, main.cpp:638).
+ * Of a decoded codeword the host already holds every received symbol: only the erased systematic symbols are
+ * news.  h_cw [B][n][S] must be PAGE-LOCKED host memory (cudaHostAlloc / cudaHostRegister; LDPC_ERR_ARG otherwise):
+ * the device fetches the RECEIVED symbols from it (erased ones are not read: they count as all-zero, the input
+ * convention above), decodes, and writes every systematic symbol whose mask bit is set back into it -- the recovered
+ * value, or zero for a symbol that stays erased.  Received symbols and the parity part are not touched.  About
+ * (1-p)*n*S up and p*k*S down instead of n*S and k*S bytes per codeword cross PCIe.
+ * ldpc_encode_host_inplace: h_cw [B][n][S] with the information symbols in rows 0..k-1 (pinned or pageable); only
+ * those rows are uploaded and only the n-k parity rows are written back.                                          */
+int ldpc_decode_host_inplace(ldpc_ctx *ctx, void *h_cw, const uint32_t *h_mask, uint8_t *h_fail,
+                             uint8_t *h_fail_any, int max_iter, int mode, int64_t B);
+int ldpc_decode_host_inplace_multi(ldpc_ctx *const *ctxs, int n_ctx, void *h_cw, const uint32_t *h_mask,
+                                   uint8_t *h_fail, uint8_t *h_fail_any, int max_iter, int mode, int64_t B);
+int ldpc_encode_host_inplace(ldpc_ctx *ctx, void *h_cw, int64_t B);
+
 /* ---- synthetic payload --------------------------------------------------------------
  * Counter-based uniform bytes (Threefry key {2, seed}, counter = 16-byte block index +
  * block0): bench / test input generator, independent of batch sharding.                  */

@@ -12,7 +12,7 @@ SO_PATH = os.path.join(HERE, "libldpc_cuda.so")
 EXPORTS = [
     "ldpc_ctx_create", "ldpc_ctx_destroy", "ldpc_ctx_info", "ldpc_read_h_file", "ldpc_ctx_get_csr", "ldpc_ctx_set_exec_geometry",
     "ldpc_encode", "ldpc_gen_erasures", "ldpc_decode", "ldpc_decode_ex", "ldpc_simulate_fer", "ldpc_get_stats", "ldpc_reset_stats",
-    "ldpc_encode_host", "ldpc_decode_host", "ldpc_decode_host_ex", "ldpc_encode_host_multi", "ldpc_decode_host_multi", "ldpc_fill_random", "ldpc_packetize", "ldpc_depacketize", "ldpc_ready_to_decode", "ldpc_packetize_var", "ldpc_depacketize_var", "ldpc_rx_stream_create", "ldpc_rx_stream_destroy", "ldpc_rx_stream_push", "ldpc_rx_stream_flush", "ldpc_rx_stream_state", "ldpc_profile_enable", "ldpc_profile_read",
+    "ldpc_encode_host", "ldpc_decode_host", "ldpc_decode_host_ex", "ldpc_encode_host_multi", "ldpc_decode_host_multi", "ldpc_decode_host_inplace", "ldpc_decode_host_inplace_multi", "ldpc_encode_host_inplace", "ldpc_fill_random", "ldpc_packetize", "ldpc_depacketize", "ldpc_ready_to_decode", "ldpc_packetize_var", "ldpc_depacketize_var", "ldpc_rx_stream_create", "ldpc_rx_stream_destroy", "ldpc_rx_stream_push", "ldpc_rx_stream_flush", "ldpc_rx_stream_state", "ldpc_profile_enable", "ldpc_profile_read",
     "rs_ctx_create", "rs_ctx_destroy", "rs_ctx_get_generator", "rs_encode", "rs_decode",
     "ldpc_nb_ctx_create", "ldpc_nb_ctx_destroy", "ldpc_nb_get_coefficients", "ldpc_nb_encode", "ldpc_nb_decode",
     "ldpc_h_generate", "ldpc_h_count_short_cycles", "ldpc_h_last_error_string",
@@ -80,6 +80,9 @@ def load():
     lib.ldpc_decode_host_ex.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i64]
     lib.ldpc_encode_host_multi.argtypes = [C.POINTER(vp), i32, vp, vp, i64]
     lib.ldpc_decode_host_multi.argtypes = [C.POINTER(vp), i32, vp, vp, vp, vp, vp, i32, i32, i64]
+    lib.ldpc_decode_host_inplace.argtypes = [vp, vp, vp, vp, vp, i32, i32, i64]
+    lib.ldpc_decode_host_inplace_multi.argtypes = [C.POINTER(vp), i32, vp, vp, vp, vp, i32, i32, i64]
+    lib.ldpc_encode_host_inplace.argtypes = [vp, vp, i64]
     lib.ldpc_fill_random.argtypes = [vp, i64, u32, u64, i32, vp]
     lib.ldpc_packetize.argtypes = [vp, vp, u32, i64, vp, vp]
     lib.ldpc_depacketize.argtypes = [vp, vp, i64, u32, i64, vp, vp, vp, vp]

@@ -177,6 +177,23 @@ class LdpcCodec:
                                              {"peel": MODE_PEEL, "hybrid": MODE_HYBRID}[mode], B))
         return out, fail
 
+    def decode_host_inplace(self, cw: torch.Tensor, mask: torch.Tensor, max_iter=50, mode="peel", fail=None, fail_any=None):
+        """ldpc_decode_host_inplace: cw is a PINNED host tensor [B, n, S]; its erased systematic symbols are overwritten with
+        what decode_host would have returned for them, nothing else crosses PCIe on the way back.  Returns (fail, fail_any)."""
+        assert not cw.is_cuda and cw.dtype == torch.uint8 and cw.is_contiguous()
+        B = cw.shape[0]
+        if fail is None:
+            fail = torch.empty((B,), dtype=torch.uint8, pin_memory=True)
+        _lib.check(self.lib.ldpc_decode_host_inplace(self._h, _ptr(cw), _ptr(mask), _ptr(fail), _ptr(fail_any), max_iter,
+                                                     {"peel": MODE_PEEL, "hybrid": MODE_HYBRID}[mode], B))
+        return fail, fail_any
+
+    def encode_host_inplace(self, cw: torch.Tensor):
+        """ldpc_encode_host_inplace: cw [B, n, S] on the host with the information symbols in rows 0..k-1; the parity rows are filled in."""
+        assert not cw.is_cuda and cw.dtype == torch.uint8 and cw.is_contiguous() and cw.shape[1] == self.n
+        _lib.check(self.lib.ldpc_encode_host_inplace(self._h, _ptr(cw), cw.shape[0]))
+        return cw
+
     def encode_host(self, info: torch.Tensor, out=None):
         assert not info.is_cuda and info.dtype == torch.uint8 and info.is_contiguous()
         B = info.shape[0]
@@ -222,6 +239,19 @@ def decode_host_multi(codecs, cw: torch.Tensor, mask: torch.Tensor, max_iter=50,
     _lib.check(c0.lib.ldpc_decode_host_multi(arr, len(codecs), _ptr(cw), _ptr(mask), _ptr(out), _ptr(fail), _ptr(fail_any), max_iter,
                                              {"peel": MODE_PEEL, "hybrid": MODE_HYBRID}[mode], B))
     return out, fail
+
+
+def decode_host_inplace_multi(codecs, cw: torch.Tensor, mask: torch.Tensor, max_iter=50, mode="peel", fail=None, fail_any=None):
+    """ldpc_decode_host_inplace_multi: the in-place form of decode_host_multi (cw pinned, repaired where it lies)."""
+    c0 = codecs[0]
+    assert not cw.is_cuda and cw.dtype == torch.uint8 and cw.is_contiguous()
+    B = cw.shape[0]
+    if fail is None:
+        fail = torch.empty((B,), dtype=torch.uint8, pin_memory=True)
+    arr = (C.c_void_p * len(codecs))(*[c._h for c in codecs])
+    _lib.check(c0.lib.ldpc_decode_host_inplace_multi(arr, len(codecs), _ptr(cw), _ptr(mask), _ptr(fail), _ptr(fail_any), max_iter,
+                                                     {"peel": MODE_PEEL, "hybrid": MODE_HYBRID}[mode], B))
+    return fail, fail_any
 
 
 def encode_host_multi(codecs, info: torch.Tensor, out=None):

@@ -22,6 +22,7 @@
 #include "erasure_gen.cuh"
 #include "hmat.hpp"
 #include "fec_packets.cuh"
+#include "host_inplace.cuh"
 #include "hybrid_ge.cuh"
 #include "nb_ldpc.cuh"
 #include "payload_exec.cuh"
@@ -1264,10 +1265,12 @@ extern "C" int ldpc_encode_host(ldpc_ctx *c, const void *h_info, void *h_cw, int
     return LDPC_OK;
 }
 
-extern "C" int ldpc_decode_host_ex(ldpc_ctx *c, const void *h_cw, const uint32_t *h_mask, void *h_out, uint8_t *h_fail,
-                                   uint8_t *h_fail_any, int max_iter, int mode, int64_t B)
+// h_out != NULL: the reference's run() -- the k systematic symbols of every codeword are copied back.
+// h_out == NULL (in place): only the symbols that were erased are written, by a kernel, straight into the caller's
+// page-locked codeword buffer (d_hcw = that buffer as the device sees it).
+static int decode_host_impl(ldpc_ctx *c, const void *h_cw, uint8_t *d_hcw, const uint32_t *h_mask, void *h_out, uint8_t *h_fail,
+                            uint8_t *h_fail_any, int max_iter, int mode, int64_t B)
 {
-    if (!c || !h_cw || !h_mask || !h_out || B < 0) return fail(LDPC_ERR_ARG, "bad argument to ldpc_decode_host");
     CUDA_TRY(cudaSetDevice(c->device));
     int rc = ensure_host_pipeline(c);
     if (rc) return rc;
@@ -1276,21 +1279,102 @@ extern "C" int ldpc_decode_host_ex(ldpc_ctx *c, const void *h_cw, const uint32_t
     // after the pair of chunk i by an event, while the copies on either side overlap freely
     int i = 0;
     bool have_ev = false;
+    // In place, the way up: gather_received_kernel fetches the received symbols itself (2 CTAs per SM measured best: 328 against
+    // 313 Gbit/s with the plain copy of whole codewords; device-initiated reads reach ~44 GB/s on this link, the copy engine
+    // 52, but 20 % fewer bytes cross).  LDPC_CUDA_HOST_GATHER = CTAs per SM of that kernel, 0 = plain copy.
+    int gather = 2;
+    if (const char *e = getenv("LDPC_CUDA_HOST_GATHER")) gather = std::max(0, std::min(8, atoi(e)));
     for (long long b0 = 0; b0 < B; b0 += c->host_chunk, i ^= 1) {
         const long long nb = std::min<long long>(c->host_chunk, B - b0);
         cudaStream_t st = c->hstream[i];
-        CUDA_TRY(cudaMemcpyAsync(c->h_in[i], static_cast<const uint8_t *>(h_cw) + size_t(b0) * in_cw, size_t(nb) * in_cw,
-                                 cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemcpyAsync(c->h_mask[i], h_mask + size_t(b0) * c->NW, size_t(nb) * c->NW * 4, cudaMemcpyHostToDevice, st));
+        if (d_hcw && gather) {
+            ldpc::GatherParams gp;
+            gp.src = d_hcw + size_t(b0) * in_cw; gp.mask = c->h_mask[i]; gp.dst = c->h_in[i]; gp.B = nb;
+            gp.n = c->code.n; gp.S = c->S; gp.NW = c->NW;
+            ldpc::gather_received_kernel<<<c->num_sms * gather, 256, 0, st>>>(gp);
+            CUDA_TRY(cudaGetLastError());
+            c->launches[LDPC_K_CHANNEL]++;
+        } else {
+            CUDA_TRY(cudaMemcpyAsync(c->h_in[i], static_cast<const uint8_t *>(h_cw) + size_t(b0) * in_cw, size_t(nb) * in_cw,
+                                     cudaMemcpyHostToDevice, st));
+        }
         if (have_ev) CUDA_TRY(cudaStreamWaitEvent(st, c->h_ev, 0));
         rc = ldpc_decode_ex(c, c->h_in[i], c->h_mask[i], c->h_out[i], c->h_fail[i], h_fail_any ? c->h_fail_any[i] : nullptr, max_iter, mode, nb, st);
         if (rc) return rc;
         CUDA_TRY(cudaEventRecord(c->h_ev, st));
         have_ev = true;
-        CUDA_TRY(cudaMemcpyAsync(static_cast<uint8_t *>(h_out) + size_t(b0) * out_cw, c->h_out[i], size_t(nb) * out_cw,
-                                 cudaMemcpyDeviceToHost, st));
+        if (h_out) {
+            CUDA_TRY(cudaMemcpyAsync(static_cast<uint8_t *>(h_out) + size_t(b0) * out_cw, c->h_out[i], size_t(nb) * out_cw,
+                                     cudaMemcpyDeviceToHost, st));
+        } else {
+            ldpc::WritebackParams wp;
+            wp.out = c->h_out[i]; wp.mask = c->h_mask[i]; wp.dst = d_hcw + size_t(b0) * in_cw; wp.B = nb;
+            wp.k = c->code.k; wp.n = c->code.n; wp.S = c->S; wp.NW = c->NW;
+            const int grid = int(std::min<long long>((nb + 7) / 8, (long long)c->num_sms * 8));
+            ldpc::writeback_erased_kernel<<<grid, 256, 0, st>>>(wp);
+            CUDA_TRY(cudaGetLastError());
+            c->launches[LDPC_K_CHANNEL]++;
+        }
         if (h_fail) CUDA_TRY(cudaMemcpyAsync(h_fail + b0, c->h_fail[i], size_t(nb), cudaMemcpyDeviceToHost, st));
         if (h_fail_any) CUDA_TRY(cudaMemcpyAsync(h_fail_any + b0, c->h_fail_any[i], size_t(nb), cudaMemcpyDeviceToHost, st));
+    }
+    CUDA_TRY(cudaStreamSynchronize(c->hstream[0]));
+    CUDA_TRY(cudaStreamSynchronize(c->hstream[1]));
+    return LDPC_OK;
+}
+
+extern "C" int ldpc_decode_host_ex(ldpc_ctx *c, const void *h_cw, const uint32_t *h_mask, void *h_out, uint8_t *h_fail,
+                                   uint8_t *h_fail_any, int max_iter, int mode, int64_t B)
+{
+    if (!c || !h_cw || !h_mask || !h_out || B < 0) return fail(LDPC_ERR_ARG, "bad argument to ldpc_decode_host");
+    return decode_host_impl(c, h_cw, nullptr, h_mask, h_out, h_fail, h_fail_any, max_iter, mode, B);
+}
+
+// the caller's buffer as the device sees it; an error unless it is page-locked host memory
+static int mapped_host_pointer(ldpc_ctx *c, void *h, const char *what, uint8_t **d)
+{
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaPointerAttributes at;
+    cudaError_t e = cudaPointerGetAttributes(&at, h);
+    if (e != cudaSuccess || at.type != cudaMemoryTypeHost || !at.devicePointer) {
+        cudaGetLastError();
+        return fail(LDPC_ERR_ARG, std::string(what) + ": the codeword buffer must be page-locked host memory (cudaHostAlloc / cudaHostRegister): "
+                                                       "the device writes into it");
+    }
+    *d = static_cast<uint8_t *>(at.devicePointer);
+    return LDPC_OK;
+}
+
+extern "C" int ldpc_decode_host_inplace(ldpc_ctx *c, void *h_cw, const uint32_t *h_mask, uint8_t *h_fail, uint8_t *h_fail_any,
+                                        int max_iter, int mode, int64_t B)
+{
+    if (!c || !h_cw || !h_mask || B < 0) return fail(LDPC_ERR_ARG, "bad argument to ldpc_decode_host_inplace");
+    if (B == 0) return LDPC_OK;
+    uint8_t *d = nullptr;
+    int rc = mapped_host_pointer(c, h_cw, "ldpc_decode_host_inplace", &d);
+    if (rc) return rc;
+    return decode_host_impl(c, h_cw, d, h_mask, nullptr, h_fail, h_fail_any, max_iter, mode, B);
+}
+
+// Encoder in place: h_cw [B][n][S] holds the information symbols in its first k rows; only those go up (a strided
+// copy) and only the n-k parity rows come back.
+extern "C" int ldpc_encode_host_inplace(ldpc_ctx *c, void *h_cw, int64_t B)
+{
+    if (!c || !h_cw || B < 0) return fail(LDPC_ERR_ARG, "bad argument to ldpc_encode_host_inplace");
+    CUDA_TRY(cudaSetDevice(c->device));
+    int rc = ensure_host_pipeline(c);
+    if (rc) return rc;
+    const size_t info_cw = size_t(c->code.k) * c->S, cw_b = size_t(c->code.n) * c->S, par_cw = cw_b - info_cw;
+    int i = 0;
+    for (long long b0 = 0; b0 < B; b0 += c->host_chunk, i ^= 1) {
+        const long long nb = std::min<long long>(c->host_chunk, B - b0);
+        cudaStream_t st = c->hstream[i];
+        uint8_t *h = static_cast<uint8_t *>(h_cw) + size_t(b0) * cw_b;
+        CUDA_TRY(cudaMemcpy2DAsync(c->h_in[i], info_cw, h, cw_b, info_cw, size_t(nb), cudaMemcpyHostToDevice, st));
+        rc = ldpc_encode(c, c->h_in[i], c->h_out[i], nb, st);
+        if (rc) return rc;
+        CUDA_TRY(cudaMemcpy2DAsync(h + info_cw, cw_b, c->h_out[i] + info_cw, cw_b, par_cw, size_t(nb), cudaMemcpyDeviceToHost, st));
     }
     CUDA_TRY(cudaStreamSynchronize(c->hstream[0]));
     CUDA_TRY(cudaStreamSynchronize(c->hstream[1]));
@@ -1355,6 +1439,17 @@ extern "C" int ldpc_decode_host_multi(ldpc_ctx *const *ctxs, int n_ctx, const vo
         return ldpc_decode_host_ex(c, static_cast<const uint8_t *>(h_cw) + size_t(b0) * in_cw, h_mask + size_t(b0) * c->NW,
                                    static_cast<uint8_t *>(h_out) + size_t(b0) * out_cw, h_fail ? h_fail + b0 : nullptr,
                                    h_fail_any ? h_fail_any + b0 : nullptr, max_iter, mode, nb);
+    });
+}
+
+extern "C" int ldpc_decode_host_inplace_multi(ldpc_ctx *const *ctxs, int n_ctx, void *h_cw, const uint32_t *h_mask, uint8_t *h_fail,
+                                              uint8_t *h_fail_any, int max_iter, int mode, int64_t B)
+{
+    if (!h_cw || !h_mask) return fail(LDPC_ERR_ARG, "NULL buffer passed to ldpc_decode_host_inplace_multi");
+    return fan_out(ctxs, n_ctx, B, "ldpc_decode_host_inplace_multi", [&](ldpc_ctx *c, int64_t b0, int64_t nb) {
+        const size_t in_cw = size_t(c->code.n) * c->S;
+        return ldpc_decode_host_inplace(c, static_cast<uint8_t *>(h_cw) + size_t(b0) * in_cw, h_mask + size_t(b0) * c->NW,
+                                        h_fail ? h_fail + b0 : nullptr, h_fail_any ? h_fail_any + b0 : nullptr, max_iter, mode, nb);
     });
 }
 

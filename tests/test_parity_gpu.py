@@ -900,3 +900,69 @@ def test_rx_stream_two_buffer_state_machine(codecs, mode, it, loss):
     for b in range(NB):
         if (block0 + b) & 0xFF in decoded:
             assert np.array_equal(decoded[(block0 + b) & 0xFF], _np(info)[b])
+
+
+# ---- in-place host entry points: only the recovered symbols come back over PCIe ------------------------------------------
+@pytest.mark.parametrize("ci,S,B,P,mode,it", [(1, 64, 700, 13, "peel", 50), (1, 64, 300, 13, "hybrid", 10), (0, 1024, 40, 19, "peel", 50),
+                                              (1, 48, 130, 12, "peel", 3), (2, 16, 90, 14, "hybrid", 10)])
+def test_decode_host_inplace_repairs_the_callers_buffer(codecs, ci, S, B, P, mode, it):
+    """ldpc_decode_host_inplace: after the call the systematic rows of the pinned codeword buffer equal the decoder output of
+    the oracle, the parity rows and every received symbol are untouched; chunked (max_batch < B) like the copying form."""
+    from ldpc_erasure_codes_b200.codec import pack_mask
+    codec = codecs(ci, S, max_batch=256)
+    code = orc.Code.builtin(ci)
+    info = _rand_info(B, codec.k, S, seed=31)
+    cw = orc.encode(code, _np(info))
+    flags = orc.gen_erasures_iid(code.n, 9, B, P=P)
+    rx = cw.copy()
+    rx[flags == 1] = 0
+    h_rx = torch.from_numpy(rx.copy()).pin_memory()
+    h_mask = torch.from_numpy(pack_mask(flags)).pin_memory()
+    fail_any = torch.zeros(B, dtype=torch.uint8).pin_memory()
+    fail, _ = codec.decode_host_inplace(h_rx, h_mask, max_iter=it, mode=mode, fail_any=fail_any)
+    ref = orc.decode(code, rx, flags, max_iter=it, mode=mode)
+    got = h_rx.numpy()
+    assert np.array_equal(got[:, :code.k], ref["out"])
+    assert np.array_equal(got[:, code.k:], rx[:, code.k:])
+    assert np.array_equal(fail.numpy(), ref["fail_sys"])
+    assert np.array_equal(fail_any.numpy(), (ref["erased"].max(axis=1) > 0).astype(np.uint8))
+    # the copying form returns the same bytes
+    out2, fail2 = codec.decode_host(torch.from_numpy(rx).pin_memory(), h_mask, max_iter=it, mode=mode)
+    assert np.array_equal(out2.numpy(), got[:, :code.k]) and np.array_equal(fail2.numpy(), fail.numpy())
+
+
+def test_host_inplace_encode_multi_and_pageable_memory(codecs):
+    from ldpc_erasure_codes_b200 import _lib as L
+    from ldpc_erasure_codes_b200.codec import LdpcCodec, decode_host_inplace_multi, pack_mask
+    codec = codecs(1, 64, max_batch=256)
+    code = orc.Code.builtin(1)
+    B = 600
+    info = _rand_info(B, codec.k, 64, seed=8)
+    # encoder in place: information rows in, parity rows filled; pageable and pinned memory both work (plain copies)
+    ref_cw = orc.encode(code, _np(info))
+    for pin in (True, False):
+        h = torch.zeros((B, code.n, 64), dtype=torch.uint8)
+        h[:, :code.k] = info.cpu()
+        h = h.pin_memory() if pin else h
+        codec.encode_host_inplace(h)
+        assert np.array_equal(h.numpy(), ref_cw)
+    # the in-place decoder writes from the device: pageable memory is refused, nothing is touched
+    flags = orc.gen_erasures_iid(code.n, 3, B, P=12)
+    rx = ref_cw.copy()
+    rx[flags == 1] = 0
+    h_mask = torch.from_numpy(pack_mask(flags)).pin_memory()
+    pageable = torch.from_numpy(rx.copy())
+    with pytest.raises(L.LdpcCudaError):
+        codec.decode_host_inplace(pageable, h_mask)
+    assert np.array_equal(pageable.numpy(), rx)
+    # several contexts on one pinned buffer
+    ndev = max(1, min(torch.cuda.device_count(), 4))
+    devs = list(range(ndev)) if ndev > 1 else [0, 0]
+    cs = [LdpcCodec(code=1, symbol_bytes=64, device=d, max_batch=128) for d in devs]
+    h_rx = torch.from_numpy(rx.copy()).pin_memory()
+    fail, _ = decode_host_inplace_multi(cs, h_rx, h_mask)
+    ref = orc.decode(code, rx, flags, max_iter=50)
+    assert np.array_equal(h_rx.numpy()[:, :code.k], ref["out"]) and np.array_equal(fail.numpy(), ref["fail_sys"])
+    assert np.array_equal(h_rx.numpy()[:, code.k:], rx[:, code.k:])
+    for c in cs:
+        c.close()
