@@ -79,6 +79,9 @@ static const bool g_tma4 = [] { const char *e = getenv("LDPC_CUDA_TMA4"); return
 // LDPC_CUDA_EXEC_PLAIN=1: the executor applies per-codeword schedules level by level with full-row gathers (the form it
 // falls back to when a blob leaves no room for its pass table; tests compare it with the bulk + walk form)
 static bool exec_plain() { const char *e = getenv("LDPC_CUDA_EXEC_PLAIN"); return e && *e && *e != '0'; }
+// LDPC_CUDA_ENC_SPLIT_STORE=0: the encoder stores a codeword in one piece after its first level and re-stores the walk's rows
+// (the decoder's way) instead of information boxes early / parity boxes late
+static bool exec_split_store() { const char *e = getenv("LDPC_CUDA_ENC_SPLIT_STORE"); return !(e && *e == '0'); }
 
 // LDPC_CUDA_DEBUG_SYNC=1: synchronise after every launch so that a faulting kernel is named
 static int debug_sync(const char *what, cudaStream_t st)
@@ -136,14 +139,15 @@ static int make_map(CUtensorMap *map, const void *base, int S, int rows, long lo
 // The same memory seen as [B][nfull][256][S], nfull = rows / 256 whole boxes per codeword: ONE tensor copy with box
 // {W, 256, nfull, 1} moves what nfull 3-D boxes move (the TMA unit takes a few hundred cycles per request; a unit
 // of the executor issued 8 + 6 of them).  Rows past nfull * 256 stay with the 3-D map, whose bounds clip them.
-static int make_map4(CUtensorMap *map, const void *base, int S, int rows, long long B, int W, int nfull, bool is_load)
+static int make_map4(CUtensorMap *map, const void *base, int S, int rows, long long B, int W, int nfull, bool is_load, int boxn = 0)
 {
+    if (boxn <= 0) boxn = nfull;      // boxes per copy (the encoder stores the whole boxes of a codeword in two parts)
     PFN_encodeTiled enc;
     int rc = get_encode_fn(&enc);
     if (rc) return rc;
     cuuint64_t dims[4] = {cuuint64_t(S), cuuint64_t(kBoxRows), cuuint64_t(nfull), cuuint64_t(B)};
     cuuint64_t strides[3] = {cuuint64_t(S), cuuint64_t(S) * kBoxRows, cuuint64_t(S) * cuuint64_t(rows)};
-    cuuint32_t box[4] = {cuuint32_t(W), cuuint32_t(kBoxRows), cuuint32_t(nfull), 1u};
+    cuuint32_t box[4] = {cuuint32_t(W), cuuint32_t(kBoxRows), cuuint32_t(boxn), 1u};
     cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void *>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -154,7 +158,7 @@ static int make_map4(CUtensorMap *map, const void *base, int S, int rows, long l
 }
 
 struct ldpc_ctx;
-static int cached_map(ldpc_ctx *c, CUtensorMap *out, const void *base, int rows, long long B, int W, int nfull, bool is_load);
+static int cached_map(ldpc_ctx *c, CUtensorMap *out, const void *base, int rows, long long B, int W, int nfull, bool is_load, int boxn = 0);
 
 // ------------------------------------------------------------------------------------------
 // context
@@ -206,7 +210,7 @@ struct ldpc_ctx {
     uint8_t *h_fail_any[2] = {nullptr, nullptr};
     cudaEvent_t h_ev = nullptr;              // orders the kernels of consecutive host-pipeline stages (they share the scratch)
     // tensor maps of recent executor launches (cuTensorMapEncodeTiled is a driver call on the small-batch latency path)
-    struct MapKey { const void *base; int rows, W, nfull, is_load; long long B; };
+    struct MapKey { const void *base; int rows, W, nfull, is_load; long long B; int boxn; };
     struct MapRec { MapKey key; CUtensorMap map; };
     std::vector<MapRec> map_cache;
     // profiling
@@ -231,16 +235,18 @@ struct ProfScope {
 };
 
 // nfull == 0: the 3-D map; else the 4-D map over whole boxes
-static int cached_map(ldpc_ctx *c, CUtensorMap *out, const void *base, int rows, long long B, int W, int nfull, bool is_load)
+static int cached_map(ldpc_ctx *c, CUtensorMap *out, const void *base, int rows, long long B, int W, int nfull, bool is_load, int boxn)
 {
+    if (boxn <= 0) boxn = nfull;
     for (const auto &r : c->map_cache)
-        if (r.key.base == base && r.key.rows == rows && r.key.B == B && r.key.W == W && r.key.nfull == nfull && r.key.is_load == int(is_load)) {
+        if (r.key.base == base && r.key.rows == rows && r.key.B == B && r.key.W == W && r.key.nfull == nfull && r.key.is_load == int(is_load) &&
+            r.key.boxn == boxn) {
             *out = r.map;
             return LDPC_OK;
         }
     ldpc_ctx::MapRec rec;
-    rec.key = {base, rows, W, nfull, int(is_load), B};
-    int rc = nfull ? make_map4(&rec.map, base, c->S, rows, B, W, nfull, is_load) : make_map(&rec.map, base, c->S, rows, B, W, is_load);
+    rec.key = {base, rows, W, nfull, int(is_load), B, boxn};
+    int rc = nfull ? make_map4(&rec.map, base, c->S, rows, B, W, nfull, is_load, boxn) : make_map(&rec.map, base, c->S, rows, B, W, is_load);
     if (rc) return rc;
     if (c->map_cache.size() >= 64) c->map_cache.erase(c->map_cache.begin());
     c->map_cache.push_back(rec);
@@ -557,7 +563,8 @@ extern "C" int ldpc_ctx_set_exec_geometry(ldpc_ctx *c, int slice_bytes, int slot
 // ------------------------------------------------------------------------------------------
 // executor launch
 // ------------------------------------------------------------------------------------------
-typedef void (*ExecKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const ExecParams);
+typedef void (*ExecKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
+                           const ExecParams);
 
 // instantiated member counts: 7 / 14 are the committed codes' maximum row weights
 static ExecKernel pick_exec(int W, int max_row_weight, int *rwm_out)
@@ -597,7 +604,17 @@ static int launch_exec(ldpc_ctx *c, const ExecGeom &g, const void *d_in, int row
     in4_map = in_map; out4_map = out_map;      // (placeholders when there is no whole box)
     if (nfull_in) { rc = cached_map(c, &in4_map, d_in, rows_in, B, g.W, nfull_in, true); if (rc) return rc; }
     if (nfull_out) { rc = cached_map(c, &out4_map, d_out, rows_out, B, g.W, nfull_out, false); if (rc) return rc; }
+    // The encoder never changes its information rows: the whole boxes below row k are stored as soon as they are loaded (outA),
+    // the boxes that hold parity rows after the walk (outB and the partial box) -- no second store of the walk's rows.
+    CUtensorMap outA_map = out4_map, outB_map = out4_map;
+    int early = (!sched_stride && nfull_out && exec_split_store()) ? std::min(rows_in / kBoxRows, nfull_out) : 0;
+    if (early) {
+        rc = cached_map(c, &outA_map, d_out, rows_out, B, g.W, nfull_out, false, early);
+        if (rc) return rc;
+        if (nfull_out > early) { rc = cached_map(c, &outB_map, d_out, rows_out, B, g.W, nfull_out, false, nfull_out - early); if (rc) return rc; }
+    }
     ExecParams p;
+    p.early_boxes = early;
     p.synd = d_synd; p.mask = d_mask; p.NW = c->NW; p.nfull_in = nfull_in; p.nfull_out = nfull_out;
     p.rows = sched_stride ? c->d_rows_dec : c->d_rows_enc; p.sched = sched; p.sched_len = sched_len; p.B = B; p.sched_stride = sched_stride;
     p.sched_max = g.sched_area; p.m = c->code.m; p.RW = c->code.RW; p.rows_in = rows_in; p.rows_out = rows_out;
@@ -613,7 +630,7 @@ static int launch_exec(ldpc_ctx *c, const ExecGeom &g, const void *d_in, int row
     const int grid = int(std::min<long long>(c->num_sms, B));
     {
         ProfScope ps(c, sched_stride ? LDPC_K_EXEC_DECODE : LDPC_K_EXEC_ENCODE, st);
-        k<<<grid, g.nslot * kExecWarpsPerGroup * 32, g.smem_bytes, st>>>(in_map, out_map, in4_map, out4_map, p);
+        k<<<grid, g.nslot * kExecWarpsPerGroup * 32, g.smem_bytes, st>>>(in_map, out_map, in4_map, out4_map, outA_map, outB_map, p);
     }
     CUDA_TRY(cudaGetLastError());
     return debug_sync(sched_stride ? "payload_exec_kernel(decode)" : "payload_exec_kernel(encode)", st);

@@ -81,6 +81,7 @@ struct ExecParams {
     uint8_t *out;               // [B][rows_out][S]: the output the tensor maps describe (the walk's symbols are re-stored with plain stores)
     int S;
     int nfull_in, nfull_out;    // whole 256-row boxes moved by ONE 4-D tensor copy (map [B][rows/256][256][S]); the rest box by box
+    int early_boxes;            // static schedule (encoder): whole boxes below row rows_in, stored as soon as they are loaded (0 = off)
     unsigned long long *phase_cycles;  // tuning aid (nullptr = off): [0] claim+issue, [1] load wait, [2] level walk, [3] store, [4] units, [5] zeroing + bulk gather, [6] walk passes
 };
 
@@ -103,7 +104,8 @@ __device__ __forceinline__ void sts128(uint32_t addr, const uint4 v)
 template <int W, int RWM>  // W = slice bytes; RWM = members gathered per check (>= max row weight)
 __global__ void __launch_bounds__(kExecMaxGroups *kExecWarpsPerGroup * 32, 1)
 payload_exec_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap out_map,
-                    const __grid_constant__ CUtensorMap in4_map, const __grid_constant__ CUtensorMap out4_map, const ExecParams p)
+                    const __grid_constant__ CUtensorMap in4_map, const __grid_constant__ CUtensorMap out4_map,
+                    const __grid_constant__ CUtensorMap outA_map, const __grid_constant__ CUtensorMap outB_map, const ExecParams p)
 {
     constexpr int RWQ = (RWM + 7) / 8;                // uint4 chunks of a padded check row
     constexpr int LPG = W / 16;                       // lanes per entry
@@ -333,6 +335,12 @@ payload_exec_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
         mbar_wait(&full[g], phase);
         phase ^= 1u;
         lap(1);
+        const bool split = p.early_boxes > 0;      // encoder: information boxes go out now, the boxes with parity rows after the walk
+        if (split && leader) {
+            const long long b = blockIdx.x + (long long)(j / p.slices) * gridDim.x;
+            tma_store_4d(&outA_map, slot, (j % p.slices) * W, 0, 0, int(b));
+            bulk_commit();
+        }
 
         const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
         const bool resid = p.synd && (hdr[2] & 0xFFFFu) != 0u;     // (uniform over the group)
@@ -406,7 +414,7 @@ payload_exec_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
         // Every symbol the schedule does not produce, and every symbol of the first level, is final: the first
         // rows_out rows go out NOW, while the level walk runs; the symbols the walk produces (holding s_i, or whatever the
         // asynchronous read catches) are stored again below, after this store has completed.
-        if (leader) {
+        if (leader && !split) {
             const long long b = blockIdx.x + (long long)(j / p.slices) * gridDim.x;
             const int sl = j % p.slices;
             if (p.nfull_out) tma_store_4d(&out4_map, slot, sl * W, 0, 0, int(b));
@@ -479,7 +487,21 @@ payload_exec_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
             if (p.phase_cycles && (tg & 31) == 0) atomicAdd(&p.phase_cycles[6], mine);
         }
         // ---- the walk's symbols, recycle the slot --------------------------------
-        if (leader) {
+        if (split) {
+            fence_proxy_async_smem();           // the walk's writes -> visible to the TMA store
+            named_bar_sync(bar_id, GT);
+            if (leader) {
+                const long long b = blockIdx.x + (long long)(j / p.slices) * gridDim.x;
+                const int sl = j % p.slices;
+                if (p.nfull_out > p.early_boxes)
+                    tma_store_4d(&outB_map, slot + size_t(p.early_boxes) * kBoxRows * W, sl * W, 0, p.early_boxes, int(b));
+                for (int q = p.nfull_out; q < p.nbox_out; q++)
+                    tma_store_3d(&out_map, slot + size_t(q) * kBoxRows * W, sl * W, q * kBoxRows, int(b));
+                bulk_commit();
+                bulk_wait_read0();
+            }
+            npass = 0;                          // (nothing to store again)
+        } else if (leader) {
             if (npass > 0) bulk_wait_all0();    // the early store is complete: what follows overwrites it in global memory
             else bulk_wait_read0();             // the slot's bytes are on their way to L2; it may be overwritten now
         }
