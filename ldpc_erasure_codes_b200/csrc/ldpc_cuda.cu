@@ -201,13 +201,15 @@ struct ldpc_ctx {
     // hybrid stage
     HybridScratch hyb;
     // host-buffer pipeline
-    cudaStream_t hstream[2] = {nullptr, nullptr};
-    uint8_t *h_in[2] = {nullptr, nullptr}, *h_out[2] = {nullptr, nullptr};
-    uint32_t *h_mask[2] = {nullptr, nullptr};
-    uint8_t *h_fail[2] = {nullptr, nullptr};
+    static constexpr int kHostStages = 3;    // stages of the host pipeline (streams + staging buffers): 3 keep the link busy while a stage decodes
+    cudaStream_t hstream[kHostStages] = {};
+    uint8_t *h_in[kHostStages] = {}, *h_out[kHostStages] = {};
+    uint32_t *h_mask[kHostStages] = {};
+    uint8_t *h_fail[kHostStages] = {};
     long long host_chunk = 0;
+    int host_stages = 0;
     bool host_ready = false;
-    uint8_t *h_fail_any[2] = {nullptr, nullptr};
+    uint8_t *h_fail_any[kHostStages] = {};
     cudaEvent_t h_ev = nullptr;              // orders the kernels of consecutive host-pipeline stages (they share the scratch)
     // tensor maps of recent executor launches (cuTensorMapEncodeTiled is a driver call on the small-batch latency path)
     struct MapKey { const void *base; int rows, W, nfull, is_load; long long B; int boxn; };
@@ -1218,12 +1220,12 @@ extern "C" int ldpc_profile_read(ldpc_ctx *c, ldpc_profile *out, int reset)
 }
 
 // ------------------------------------------------------------------------------------------
-// host-buffer entry points: chunked, double-buffered over two streams so that the copy of
-// chunk i+1 overlaps the kernels and the read-back of chunk i.
+// host-buffer entry points: chunked, staged over three streams so that the copy of chunk i+1 (and i+2)
+// overlaps the kernels and the read-back of chunk i.
 // ------------------------------------------------------------------------------------------
 static void free_host_pipeline(ldpc_ctx *c)
 {
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < ldpc_ctx::kHostStages; i++) {
         if (c->hstream[i]) { cudaStreamDestroy(c->hstream[i]); c->hstream[i] = nullptr; }
         cudaFree(c->h_in[i]); cudaFree(c->h_out[i]); cudaFree(c->h_mask[i]); cudaFree(c->h_fail[i]); cudaFree(c->h_fail_any[i]);
         c->h_in[i] = nullptr; c->h_out[i] = nullptr; c->h_mask[i] = nullptr; c->h_fail[i] = nullptr; c->h_fail_any[i] = nullptr;
@@ -1242,7 +1244,9 @@ static int ensure_host_pipeline(ldpc_ctx *c)
     c->host_chunk = chunk;
     cudaError_t e = cudaSuccess;
     auto ok = [&](cudaError_t r) { if (e == cudaSuccess) e = r; return e == cudaSuccess; };
-    for (int i = 0; i < 2 && e == cudaSuccess; i++) {
+    c->host_stages = ldpc_ctx::kHostStages;            // LDPC_CUDA_HOST_STAGES=2: round 1's double buffering (A/B comparisons)
+    if (const char *es = getenv("LDPC_CUDA_HOST_STAGES")) c->host_stages = std::max(1, std::min(ldpc_ctx::kHostStages, atoi(es)));
+    for (int i = 0; i < c->host_stages && e == cudaSuccess; i++) {
         ok(cudaStreamCreateWithFlags(&c->hstream[i], cudaStreamNonBlocking));
         ok(cudaMalloc(&c->h_in[i], size_t(chunk) * per_cw));
         ok(cudaMalloc(&c->h_out[i], size_t(chunk) * per_cw));
@@ -1267,7 +1271,7 @@ extern "C" int ldpc_encode_host(ldpc_ctx *c, const void *h_info, void *h_cw, int
     if (rc) return rc;
     const size_t in_cw = size_t(c->code.k) * c->S, out_cw = size_t(c->code.n) * c->S;
     int i = 0;
-    for (long long b0 = 0; b0 < B; b0 += c->host_chunk, i ^= 1) {
+    for (long long b0 = 0; b0 < B; b0 += c->host_chunk, i = (i + 1) % c->host_stages) {
         const long long nb = std::min<long long>(c->host_chunk, B - b0);
         cudaStream_t st = c->hstream[i];
         CUDA_TRY(cudaMemcpyAsync(c->h_in[i], static_cast<const uint8_t *>(h_info) + size_t(b0) * in_cw, size_t(nb) * in_cw,
@@ -1277,8 +1281,7 @@ extern "C" int ldpc_encode_host(ldpc_ctx *c, const void *h_info, void *h_cw, int
         CUDA_TRY(cudaMemcpyAsync(static_cast<uint8_t *>(h_cw) + size_t(b0) * out_cw, c->h_out[i], size_t(nb) * out_cw,
                                  cudaMemcpyDeviceToHost, st));
     }
-    CUDA_TRY(cudaStreamSynchronize(c->hstream[0]));
-    CUDA_TRY(cudaStreamSynchronize(c->hstream[1]));
+    for (int q = 0; q < c->host_stages; q++) CUDA_TRY(cudaStreamSynchronize(c->hstream[q]));
     return LDPC_OK;
 }
 
@@ -1301,7 +1304,7 @@ static int decode_host_impl(ldpc_ctx *c, const void *h_cw, uint8_t *d_hcw, const
     // 52, but 20 % fewer bytes cross).  LDPC_CUDA_HOST_GATHER = CTAs per SM of that kernel, 0 = plain copy.
     int gather = 2;
     if (const char *e = getenv("LDPC_CUDA_HOST_GATHER")) gather = std::max(0, std::min(8, atoi(e)));
-    for (long long b0 = 0; b0 < B; b0 += c->host_chunk, i ^= 1) {
+    for (long long b0 = 0; b0 < B; b0 += c->host_chunk, i = (i + 1) % c->host_stages) {
         const long long nb = std::min<long long>(c->host_chunk, B - b0);
         cudaStream_t st = c->hstream[i];
         CUDA_TRY(cudaMemcpyAsync(c->h_mask[i], h_mask + size_t(b0) * c->NW, size_t(nb) * c->NW * 4, cudaMemcpyHostToDevice, st));
@@ -1336,8 +1339,7 @@ static int decode_host_impl(ldpc_ctx *c, const void *h_cw, uint8_t *d_hcw, const
         if (h_fail) CUDA_TRY(cudaMemcpyAsync(h_fail + b0, c->h_fail[i], size_t(nb), cudaMemcpyDeviceToHost, st));
         if (h_fail_any) CUDA_TRY(cudaMemcpyAsync(h_fail_any + b0, c->h_fail_any[i], size_t(nb), cudaMemcpyDeviceToHost, st));
     }
-    CUDA_TRY(cudaStreamSynchronize(c->hstream[0]));
-    CUDA_TRY(cudaStreamSynchronize(c->hstream[1]));
+    for (int q = 0; q < c->host_stages; q++) CUDA_TRY(cudaStreamSynchronize(c->hstream[q]));
     return LDPC_OK;
 }
 
@@ -1384,7 +1386,7 @@ extern "C" int ldpc_encode_host_inplace(ldpc_ctx *c, void *h_cw, int64_t B)
     if (rc) return rc;
     const size_t info_cw = size_t(c->code.k) * c->S, cw_b = size_t(c->code.n) * c->S, par_cw = cw_b - info_cw;
     int i = 0;
-    for (long long b0 = 0; b0 < B; b0 += c->host_chunk, i ^= 1) {
+    for (long long b0 = 0; b0 < B; b0 += c->host_chunk, i = (i + 1) % c->host_stages) {
         const long long nb = std::min<long long>(c->host_chunk, B - b0);
         cudaStream_t st = c->hstream[i];
         uint8_t *h = static_cast<uint8_t *>(h_cw) + size_t(b0) * cw_b;
@@ -1393,8 +1395,7 @@ extern "C" int ldpc_encode_host_inplace(ldpc_ctx *c, void *h_cw, int64_t B)
         if (rc) return rc;
         CUDA_TRY(cudaMemcpy2DAsync(h + info_cw, cw_b, c->h_out[i] + info_cw, cw_b, par_cw, size_t(nb), cudaMemcpyDeviceToHost, st));
     }
-    CUDA_TRY(cudaStreamSynchronize(c->hstream[0]));
-    CUDA_TRY(cudaStreamSynchronize(c->hstream[1]));
+    for (int q = 0; q < c->host_stages; q++) CUDA_TRY(cudaStreamSynchronize(c->hstream[q]));
     return LDPC_OK;
 }
 

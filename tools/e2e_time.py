@@ -25,5 +25,5 @@ ts = []
 for _ in range(R):
     t0 = time.perf_counter(); run(); ts.append(time.perf_counter() - t0)
 ts.sort()
-print(f"api={api} gather={os.environ.get('LDPC_CUDA_HOST_GATHER', '0')} chunk_mb={os.environ.get('LDPC_CUDA_HOST_CHUNK_MB', 'default')} B={B}: "
+print(f"api={api} gather={os.environ.get('LDPC_CUDA_HOST_GATHER', 'default')} chunk_mb={os.environ.get('LDPC_CUDA_HOST_CHUNK_MB', 'default')} B={B}: "
       f"{B * codec.k * S * 8 / ts[len(ts)//2] / 1e9:.1f} Gbit/s (best {B * codec.k * S * 8 / ts[0] / 1e9:.1f}), {ts[len(ts)//2]*1e3:.1f} ms", flush=True)
