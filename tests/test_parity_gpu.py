@@ -966,3 +966,35 @@ def test_host_inplace_encode_multi_and_pageable_memory(codecs):
     assert np.array_equal(h_rx.numpy()[:, code.k:], rx[:, code.k:])
     for c in cs:
         c.close()
+
+
+@pytest.mark.parametrize("env", [{"LDPC_CUDA_HOST_GATHER": "0"}, {"LDPC_CUDA_HOST_STAGES": "2"}, {"LDPC_CUDA_HOST_STAGES": "1", "LDPC_CUDA_HOST_GATHER": "4"},
+                                 {"LDPC_CUDA_ENC_SPLIT_STORE": "0"}])
+def test_host_path_switches_give_the_same_bytes(monkeypatch, env):
+    """The A/B switches of the host path and of the encoder's store select other code paths, not other results."""
+    from ldpc_erasure_codes_b200.codec import LdpcCodec, pack_mask
+    for name, v in env.items():
+        monkeypatch.setenv(name, v)
+    codec = LdpcCodec(code=1, symbol_bytes=64, device=0, max_batch=200)      # a fresh context: the pipeline is built under these settings
+    code = orc.Code.builtin(1)
+    B = 900
+    info = _rand_info(B, codec.k, 64, seed=4)
+    ref_cw = orc.encode(code, _np(info))
+    assert np.array_equal(_np(codec.encode(info)), ref_cw)
+    h = torch.zeros((B, code.n, 64), dtype=torch.uint8)
+    h[:, :code.k] = info.cpu()
+    h = h.pin_memory()
+    codec.encode_host_inplace(h)
+    assert np.array_equal(h.numpy(), ref_cw)
+    flags = orc.gen_erasures_iid(code.n, 6, B, P=13)
+    rx = ref_cw.copy()
+    rx[flags == 1] = 0
+    h_rx = torch.from_numpy(rx.copy()).pin_memory()
+    h_mask = torch.from_numpy(pack_mask(flags)).pin_memory()
+    fail, _ = codec.decode_host_inplace(h_rx, h_mask)
+    ref = orc.decode(code, rx, flags, max_iter=50)
+    assert np.array_equal(h_rx.numpy()[:, :code.k], ref["out"]) and np.array_equal(h_rx.numpy()[:, code.k:], rx[:, code.k:])
+    assert np.array_equal(fail.numpy(), ref["fail_sys"])
+    out2, fail2 = codec.decode_host(torch.from_numpy(rx).pin_memory(), h_mask)
+    assert np.array_equal(out2.numpy(), ref["out"]) and np.array_equal(fail2.numpy(), ref["fail_sys"])
+    codec.close()
