@@ -998,3 +998,27 @@ def test_host_path_switches_give_the_same_bytes(monkeypatch, env):
     out2, fail2 = codec.decode_host(torch.from_numpy(rx).pin_memory(), h_mask)
     assert np.array_equal(out2.numpy(), ref["out"]) and np.array_equal(fail2.numpy(), ref["fail_sys"])
     codec.close()
+
+
+def test_decode_host_inplace_on_registered_memory(codecs):
+    """INTEGRATION.md's route for an existing host array: cudaHostRegister it, repair it in place, unregister."""
+    from ldpc_erasure_codes_b200.codec import pack_mask
+    codec = codecs(1, 64, max_batch=256)
+    code = orc.Code.builtin(1)
+    B = 300
+    info = _rand_info(B, codec.k, 64, seed=12)
+    cw = orc.encode(code, _np(info))
+    flags = orc.gen_erasures_iid(code.n, 21, B, P=12)
+    rx = cw.copy()
+    rx[flags == 1] = 0
+    h_rx = torch.from_numpy(rx.copy())                    # pageable
+    h_mask = torch.from_numpy(pack_mask(flags))
+    rt = torch.cuda.cudart()
+    assert int(rt.cudaHostRegister(h_rx.data_ptr(), h_rx.numel(), 0)) == 0
+    try:
+        fail, _ = codec.decode_host_inplace(h_rx, h_mask)
+    finally:
+        assert int(rt.cudaHostUnregister(h_rx.data_ptr())) == 0
+    ref = orc.decode(code, rx, flags, max_iter=50)
+    assert np.array_equal(h_rx.numpy()[:, :code.k], ref["out"]) and np.array_equal(fail.numpy(), ref["fail_sys"])
+    assert np.array_equal(h_rx.numpy()[:, code.k:], rx[:, code.k:])
