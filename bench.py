@@ -450,6 +450,24 @@ def run_b200(args):
                       "symbols back into the codeword buffer)",
                "copy_out": e2e_copy}
 
+        if encode_rec is not None:
+            # the encoder through host buffers: whole buffers (ldpc_encode_host) and in place (information rows up, parity rows down)
+            h_info = h_out                                  # [eb][k][S] pinned: the decoded information of the steps above
+            enc_copy = lambda: codec.encode_host(h_info, out=h_cw)
+            enc_copy()
+            chk = codec.encode(h_info[:256].to(dev))
+            assert bool((h_cw[:256] == chk.cpu()).all())
+            dt_c = timed_host(enc_copy)
+            h_cw[:, k:].zero_()
+            enc_inpl = lambda: codec.encode_host_inplace(h_cw)
+            enc_inpl()
+            assert bool((h_cw[:256] == chk.cpu()).all())
+            dt_i = timed_host(enc_inpl)
+            encode_rec["e2e"] = {"value": world * eb * args.steps * k * S * 8 / dt_i / 1e9, "unit": "Gbit/s", "codewords_per_step": eb,
+                                 "h2d_bytes_per_step": eb * k * S, "d2h_bytes_per_step": eb * (n - k) * S, "api": "ldpc_encode_host_inplace",
+                                 "copy_out": {"value": world * eb * args.steps * k * S * 8 / dt_c / 1e9, "h2d_bytes_per_step": eb * k * S,
+                                              "d2h_bytes_per_step": eb * n * S, "api": "ldpc_encode_host"}}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         g, threads, sample, _, _ = cpu_decode_rate(args, args.seed, args.cpu_seconds, "port")
