@@ -1050,14 +1050,15 @@ inline int hybrid_prepare(HybridScratch &h, const HostCode &code, int S, int NW,
     if ((e = cudaMalloc(&h.d_list3, size_t(max_batch) * 4)) != cudaSuccess) return bad("hybrid: list", e);
     if ((e = cudaMalloc(&h.d_list4, size_t(max_batch) * 4)) != cudaSuccess) return bad("hybrid: list", e);
     if ((e = cudaMalloc(&h.d_count, 16 * 4)) != cudaSuccess) return bad("hybrid: count", e);
-    {   // warp stages: [0] inactivation decoding, slots for a typical stopping set (85 % of the checks involved);
+    {   // warp stages: [0] inactivation decoding, slots for a typical stopping set (2/3 of the checks involved);
         //              [1] the same with worst-case slots, for what [0] defers for size;
         //              [2] plain Gauss-Jordan per warp, worst-case slots: more than kInactMax inactivations
         const long long budget_w = (long long)(smem_optin - 2048) / 4;
-        // rows a typical slot holds: 85 % of m (LDPC_CUDA_GE_TYP, in %).  Measured on (2040,1530), 32 768 codewords, 10 sweeps first: at
-        // 12/64 3.16 ms with 80-90 % against 3.51 ms with 67 % (few frames stall, almost all of them then fit the first stage); at 13/64
-        // 6.08 (85 %), 6.12 (67 %), 6.5-6.6 (75, 80, 90, 100 %: one warp less per CTA without fewer deferrals)
-        int typ = 85 * code.m / 100;
+        // rows a typical slot holds: 2/3 of m (LDPC_CUDA_GE_TYP, in %).  Measured on (2040,1530), 10 sweeps first: 85 % is 10 % faster at
+        // 12/64 (3.16 against 3.51 ms per 32 768 codewords: few frames stall and almost all of them then fit the first stage) and equal at
+        // 13/64 with 32 768 codewords per chunk, but 4 % slower at 13/64 with the bench's 65 536 (184.8 against 177.8 ms per 1 Mi codewords);
+        // 75, 80, 90, 100 % are slower at 13/64 either way (one warp less per CTA without fewer deferrals)
+        int typ = 2 * code.m / 3;
         if (const char *et = getenv("LDPC_CUDA_GE_TYP")) typ = std::max(16, std::min(code.m, code.m * atoi(et) / 100));
         const int fx = ge_inact_fixed_words(code.m, NW, MW);
         const long long need[3] = {fx + ge_inact_area_words(typ, typ, code.VW, true),
